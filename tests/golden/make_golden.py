@@ -54,6 +54,25 @@ def main():
         blob["in__" + k] = v
         for c in CODECS:
             blob[f"out__{k}__{c.name}"] = ref_compress(c, v)
+    # mode-1 (single symbol) streams: only the reference's own single encoders can make them
+    # (src/rle8_extreme_cpu.h:346-700; the single encoders themselves are out of scope)
+    import ctypes
+    lib = ref_lib()
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    rng = np.random.default_rng(77)
+    for nm in ("rle8_single_compress", "rle8_packed_single_compress"):
+        f = getattr(lib, nm)
+        f.restype = ctypes.c_uint32
+        f.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32]
+        for i, n in enumerate((40, 700, 3000, 20000)):
+            data = gen_fuzz(rng, n, max_sym=1, p_run=0.6)
+            data[rng.random(n) < 0.5] = 0
+            buf = np.zeros(n + 64, dtype=np.uint8); buf[:n] = data
+            out = np.zeros(n + 1024, dtype=np.uint8)
+            r = f(buf.ctypes.data_as(u8p), n, out.ctypes.data_as(u8p), len(out))
+            assert r > 0 and out[8] == 1, (nm, n, int(out[8]))
+            blob[f"single_in__{nm}__{i}"] = data
+            blob[f"single_out__{nm}__{i}"] = out[:r].copy()
     np.savez_compressed(os.path.join(HERE, "golden_small.npz"), **blob)
     hashes = {}
     for k, v in large_inputs().items():

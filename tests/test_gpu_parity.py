@@ -1,0 +1,195 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the product's C ABI
+(libhsrle_b200.so); the checkers are the oracle (oracle/liboracle.so), the committed golden vectors
+made from the compiled reference, and -- when the prebuilt oracle/_ref travelled along -- the
+compiled reference itself."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from common import (CODECS, CODEC_BY_NAME, gen_dct, gen_fuzz, gen_run_mixed, gen_short_runs, oracle_compress,
+                    oracle_decompress, out_capacity, ref_compress, ref_decompress, ref_lib)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hs():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import hsrle_b200
+    assert hsrle_b200.lib.hsrle_device() >= 0, hsrle_b200.last_error()
+    return hsrle_b200
+
+
+def gpu_enc(hs, c, data):
+    return hs.compress(c.cname, data, out_capacity(len(data)))
+
+
+def gpu_dec(hs, c, stream, n):
+    return hs.decompress(c.dname, stream, n)
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_golden_small(hs, codec, golden_small):
+    for k in sorted(k[4:] for k in golden_small.files if k.startswith("in__")):
+        data = golden_small["in__" + k]
+        want = golden_small[f"out__{k}__{codec.name}"]
+        got = gpu_enc(hs, codec, data)
+        assert np.array_equal(got, want), f"{codec.name}: GPU stream differs from reference on {k} ({hs.last_error()})"
+        r, dec = gpu_dec(hs, codec, want, len(data))
+        assert r == len(data) and np.array_equal(dec, data), f"{codec.name}: GPU decode fails on {k}"
+
+
+@pytest.fixture(scope="module")
+def large():
+    from golden.make_golden import large_inputs
+    return large_inputs()
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_golden_hashes(hs, codec, golden_hashes, large):
+    for k, v in large.items():
+        h = golden_hashes[k]["streams"][codec.name]
+        got = gpu_enc(hs, codec, v)
+        assert len(got) == h["len"], (codec.name, k, len(got), h["len"])
+        assert hashlib.sha256(got.tobytes()).hexdigest() == h["sha256"], (codec.name, k)
+        r, dec = gpu_dec(hs, codec, got, len(v))
+        assert r == len(v) and np.array_equal(dec, v), (codec.name, k)
+
+
+SIZES = [1, 2, 3, 5, 8, 15, 16, 17, 31, 32, 33, 34, 40, 47, 48, 49, 63, 64, 65, 66, 100, 255, 256, 257, 300, 1000,
+         4095, 4096, 4097, 5000, 20000]
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_fuzz_vs_oracle(hs, codec):
+    rng = np.random.default_rng(hash(codec.name) & 0xFFFF)
+    for it in range(60):
+        n = SIZES[it % len(SIZES)] if it % 2 else int(rng.integers(1, 3000))
+        data = gen_fuzz(rng, n)
+        want = oracle_compress(codec, data)
+        got = gpu_enc(hs, codec, data)
+        assert np.array_equal(got, want), f"{codec.name}: n={n} it={it}"
+        r, dec = gpu_dec(hs, codec, want, n)
+        assert r == n and np.array_equal(dec, data), f"{codec.name}: decode n={n} it={it}"
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_edge_inputs(hs, codec):
+    """configs[4]: all-random, single symbol, alternating 1-byte / 2-byte runs, 1 KB .. 1 MB."""
+    rng = np.random.default_rng(17)
+    for n in (1024, 65536, 1 << 20):
+        for data in (rng.integers(0, 256, size=n, dtype=np.uint8), np.full(n, 0xAB, dtype=np.uint8),
+                     np.tile(np.array([1, 2], dtype=np.uint8), n // 2), np.tile(np.array([1, 1, 2, 2], dtype=np.uint8), n // 4)):
+            want = oracle_compress(codec, data)
+            got = gpu_enc(hs, codec, data)
+            assert np.array_equal(got, want), (codec.name, n)
+            r, dec = gpu_dec(hs, codec, got, n)
+            assert r == n and np.array_equal(dec, data), (codec.name, n)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle8_3symlut", "rle16_sym", "rle24_byte_packed",
+                                  "rle32_7symlut_sym", "rle48_byte", "rle64_byte_packed", "rle64_3symlut_byte"])
+def test_structured_streams(hs, name):
+    """DCT-shaped, short-run-heavy and run-mixed streams at a few MiB."""
+    codec = CODEC_BY_NAME[name]
+    for data in (gen_dct(3 << 20, seed=21), gen_short_runs(2 << 20, seed=22, W=codec.W), gen_short_runs(2 << 20, seed=23, W=1),
+                 gen_run_mixed(4 << 20, seed=24)):
+        want = oracle_compress(codec, data)
+        got = gpu_enc(hs, codec, data)
+        assert len(got) == len(want) and np.array_equal(got, want), (name, len(got), len(want))
+        r, dec = gpu_dec(hs, codec, got, len(data))
+        assert r == len(data) and np.array_equal(dec, data)
+
+
+@pytest.mark.skipif(ref_lib() is None, reason="prebuilt compiled reference not available")
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_cross_decode_with_compiled_reference(hs, codec):
+    """reference decodes GPU streams; GPU decodes reference streams."""
+    rng = np.random.default_rng(99)
+    for n in (777, 30000, 250000):
+        data = gen_fuzz(rng, n, long_every=11)
+        a = ref_compress(codec, data)
+        b = gpu_enc(hs, codec, data)
+        assert np.array_equal(a, b), (codec.name, n)
+        r, d = ref_decompress(codec, b, n)
+        assert r == n and np.array_equal(d, data)
+        r, d = gpu_dec(hs, codec, a, n)
+        assert r == n and np.array_equal(d, data)
+
+
+def test_single_mode_streams(hs, golden_small):
+    for k in [k for k in golden_small.files if k.startswith("single_in__")]:
+        _, nm, i = k.split("__")
+        data = golden_small[k]
+        stream = golden_small[f"single_out__{nm}__{i}"]
+        codec = CODEC_BY_NAME["rle8_packed_multi" if "packed" in nm else "rle8_multi"]
+        r, dec = gpu_dec(hs, codec, stream, len(data))
+        assert r == len(data) and np.array_equal(dec, data), k
+
+
+def test_error_conventions(hs):
+    """return 0 on bad arguments / headers (src/rle8_extreme_cpu.h:88,704-712,759-760)."""
+    c = CODEC_BY_NAME["rle8_multi"]
+    data = gen_dct(5000, seed=1)
+    assert len(hs.compress(c.cname, data, out_size=len(data))) == 0          # outSize < rle_compress_bounds
+    s = gpu_enc(hs, c, data)
+    assert gpu_dec(hs, c, s, len(data) - 1)[0] == 0                           # uncompressedLength > outSize
+    assert gpu_dec(hs, c, s[:-5], len(data))[0] == 0                          # compressedLength > inSize
+    bad = s.copy(); bad[8] = 7
+    assert gpu_dec(hs, c, bad, len(data))[0] == 0                             # unknown mode
+    # the decoder must not depend on bytes after compressedLength (src/rle_fuzz.c:628-633)
+    padded = np.concatenate([s, np.full(300, 0xFF, dtype=np.uint8)])
+    r, d = gpu_dec(hs, c, padded, len(data))
+    assert r == len(data) and np.array_equal(d, data)
+
+
+def test_device_resident_and_async_paths(hs):
+    import torch
+    dev = torch.device("cuda:0")
+    for name in ("rle8_multi", "rle32_byte_packed", "rle16_7symlut_sym"):
+        codec = CODEC_BY_NAME[name]
+        data = gen_dct(1 << 20, seed=5)
+        want = oracle_compress(codec, data)
+        t_in = torch.from_numpy(data).to(dev)
+        t_out = torch.empty(out_capacity(len(data)), dtype=torch.uint8, device=dev)
+        r = hs.compress_device(name, t_in, t_out)
+        assert r == len(want) and np.array_equal(t_out[:r].cpu().numpy(), want)
+        # async: caller-owned workspace, current stream, result read back afterwards
+        ws = torch.empty(hs.compress_workspace_size(name, len(data)), dtype=torch.uint8, device=dev)
+        res = torch.zeros(8, dtype=torch.int32, device=dev)
+        t_out.zero_()
+        hs.compress_device_async(name, t_in, t_out, ws, res, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        rr = res.cpu().numpy()
+        assert rr[0] == len(want) and rr[1] == 0
+        assert np.array_equal(t_out[: rr[0]].cpu().numpy(), want)
+        t_dec = torch.empty(len(data) + 128, dtype=torch.uint8, device=dev)
+        dws = torch.empty(hs.decompress_workspace_size(name, int(rr[0]), len(data)), dtype=torch.uint8, device=dev)
+        hs.decompress_device_async(name, t_out, int(rr[0]), t_dec, len(data), dws, res, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        rr = res.cpu().numpy()
+        assert rr[0] == len(data) and rr[1] == 0
+        assert np.array_equal(t_dec[: len(data)].cpu().numpy(), data)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle64_byte_packed", "rle24_3symlut_sym"])
+def test_full_size_88mb_roundtrip(hs, name):
+    """BASELINE configs[0,1] size: 88,473,600-byte DCT stream; encoder parity against the oracle and
+    encode -> decode round trip on the device."""
+    import torch
+    codec = CODEC_BY_NAME[name]
+    n = 88473600
+    data = gen_dct(n)
+    want = oracle_compress(codec, data)
+    dev = torch.device("cuda:0")
+    t_in = torch.from_numpy(data).to(dev)
+    t_out = torch.empty(out_capacity(n), dtype=torch.uint8, device=dev)
+    r = hs.compress_device(name, t_in, t_out)
+    assert r == len(want), (r, len(want), hs.last_error())
+    assert torch.equal(t_out[:r].cpu(), torch.from_numpy(want))
+    t_dec = torch.empty(n + 128, dtype=torch.uint8, device=dev)
+    rd = hs.decompress_device(name, t_out, r, t_dec, n)
+    assert rd == n
+    assert torch.equal(t_dec[:n], t_in)

@@ -37,3 +37,17 @@ def test_oracle_matches_golden_hashes(codec, golden_hashes, large):
         assert hashlib.sha256(got.tobytes()).hexdigest() == h["streams"][codec.name]["sha256"], (codec.name, k)
         r, dec = oracle_decompress(codec, got, len(v))
         assert r == len(v) and np.array_equal(dec, v)
+
+
+def test_oracle_decodes_golden_single_mode_streams(golden_small):
+    """mode-1 streams (src/rle8_extreme_cpu.h:736-757) made by the reference's single encoders."""
+    from common import CODEC_BY_NAME
+    keys = [k for k in golden_small.files if k.startswith("single_in__")]
+    assert len(keys) == 8
+    for k in keys:
+        _, nm, i = k.split("__")
+        data = golden_small[k]
+        stream = golden_small[f"single_out__{nm}__{i}"]
+        codec = CODEC_BY_NAME["rle8_packed_multi" if "packed" in nm else "rle8_multi"]
+        r, dec = oracle_decompress(codec, stream, len(data))
+        assert r == len(data) and np.array_equal(dec, data)
