@@ -17,11 +17,14 @@
 // Reference entry points this file replaces: src/rle.h:100-394 (see include/hsrle_b200.h).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
+#include <map>
 
 #include "../../include/hsrle_b200.h"
 #include "hsrle_stages.cuh"
@@ -31,9 +34,17 @@ namespace hsrle {
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
+// optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
+struct TimedLaunch { const char *name; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+
 #define HSRLE_LAUNCH(kern, grid, block, smem, stream, ...)                 \
   do {                                                                     \
+    TimedLaunch tl_{ #kern, nullptr, nullptr };                            \
+    if (g_timing) { cudaEventCreate(&tl_.a); cudaEventCreate(&tl_.b); cudaEventRecord(tl_.a, (stream)); } \
     kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+    if (g_timing) { cudaEventRecord(tl_.b, (stream)); g_timed.push_back(tl_); } \
     g_launches.fetch_add(1, std::memory_order_relaxed);                    \
   } while (0)
 
@@ -811,6 +822,33 @@ uint32_t hsrle_decompress_host(int codec, const uint8_t *pIn, uint32_t inSize, u
   if (!cuda_ok(cudaMemcpyAsync(pOut, C.dOut, r, cudaMemcpyDeviceToHost, C.stream), "D2H")) return 0;
   if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
   return r;
+}
+
+void hsrle_timing_begin(void)
+{
+  for (auto &t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  g_timed.clear(); g_timing = true;
+}
+// Synchronises the device and writes "kernel:launches:total_ms;..." for every kernel launched since
+// hsrle_timing_begin().  Returns the number of characters written.
+int hsrle_timing_end(char *buf, int bufSize)
+{
+  g_timing = false;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> acc;
+  for (auto &t : g_timed)
+  {
+    float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
+    auto &e = acc[t.name]; e.first++; e.second += ms;
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  g_timed.clear();
+  std::string out;
+  for (auto &kv : acc) { char tmp[256]; snprintf(tmp, sizeof(tmp), "%s:%d:%.6f;", kv.first.c_str(), kv.second.first, kv.second.second); out += tmp; }
+  if (!buf || bufSize <= 0) return 0;
+  const int nw = (int)std::min<size_t>(out.size(), (size_t)bufSize - 1);
+  memcpy(buf, out.data(), nw); buf[nw] = 0;
+  return nw;
 }
 
 const char *hsrle_last_error(void) { return g_err.c_str(); }

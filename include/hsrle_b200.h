@@ -198,6 +198,10 @@ const char *hsrle_last_error(void);
 int hsrle_device(void);
 /* Number of kernels the library has launched so far in this process (monotonic). */
 uint64_t hsrle_kernel_launches(void);
+/* Optional per-kernel CUDA-event timing (measurement aid): begin() arms it; end() synchronises the
+ * device and writes "kernel:launches:total_ms;..." into buf, returning the characters written. */
+void hsrle_timing_begin(void);
+int hsrle_timing_end(char *buf, int bufSize);
 
 #ifdef __cplusplus
 }
