@@ -1,0 +1,454 @@
+// hsrle_api.cu -- host side of the B200 extreme-RLE codec: C ABI, workspace carving, launch sequences.
+//
+// Reference entry points this file replaces: src/rle.h:100-394 (see include/hsrle_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/hsrle_b200.h"
+#include "hsrle_dispatch.h"
+#include "hsrle_enc_kernels.cuh"
+#include "hsrle_dec_v1_kernels.cuh"
+
+namespace hsrle {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+// optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
+struct TimedLaunch { const char *name; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+
+#define HSRLE_LAUNCH_NAMED(name, kern, grid, block, smem, stream, ...)     \
+  do {                                                                     \
+    TimedLaunch tl_{ name, nullptr, nullptr };                             \
+    if (g_timing) { cudaEventCreate(&tl_.a); cudaEventCreate(&tl_.b); cudaEventRecord(tl_.a, (stream)); } \
+    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+    if (g_timing) { cudaEventRecord(tl_.b, (stream)); g_timed.push_back(tl_); } \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                    \
+  } while (0)
+#define HSRLE_LAUNCH(kern, grid, block, smem, stream, ...) HSRLE_LAUNCH_NAMED(#kern, kern, grid, block, smem, stream, __VA_ARGS__)
+
+static bool cuda_ok(cudaError_t e, const char *what)
+{
+  if (e == cudaSuccess) return true;
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+static int g_numSM = 0;
+static int num_sms()
+{
+  if (g_numSM == 0)
+  {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_numSM = n;
+    else g_numSM = 148;
+  }
+  return g_numSM;
+}
+
+// ================================================================================================
+// host side: workspace carving + launch sequences
+struct Carver
+{
+  uint8_t *base; size_t off;
+  template <typename T> T *take(size_t count)
+  {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+static const EncKernels *enc_kernels_for(int codec)
+{
+  const int wi = codec >> 3;
+  const EncKernels *tab = nullptr;
+  switch (wi)
+  {
+    case 0: tab = enc_kernels_w1(); break; case 1: tab = enc_kernels_w2(); break; case 2: tab = enc_kernels_w3(); break;
+    case 3: tab = enc_kernels_w4(); break; case 4: tab = enc_kernels_w6(); break; case 5: tab = enc_kernels_w8(); break;
+    default: return nullptr;
+  }
+  const EncKernels *k = tab + (codec & 7);
+  return k->scan ? k : nullptr;
+}
+
+static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t *zeroBytes)
+{
+  Carver cv{ (uint8_t *)ws, 0 };
+  B.n = n;
+  B.nVec = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
+  B.lastVec = (n - 1) >> 4;
+  B.nTiles = (B.nVec + E1_TILE_VECS - 1) / E1_TILE_VECS;
+  B.maxRuns = n / (sp.minM + 1) + 2;
+  B.maxSC = B.maxRuns / E2_SCR + 2;
+  const size_t maxChunks = (size_t)B.maxSC * E2_T;
+  // zero-initialised region first: scalars + look-back status words
+  B.sc = cv.take<EncScalars>(1);
+  B.tileStatus = cv.take<unsigned long long>(B.nTiles + 1);
+  if (zeroBytes) *zeroBytes = cv.off;
+  B.runA = cv.take<uint32_t>(B.maxRuns); B.runB = cv.take<uint32_t>(B.maxRuns);
+  B.runSym = cv.take<uint64_t>(sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns);
+  B.cIn = cv.take<AutoState>(maxChunks); B.cLut = cv.take<Lut>(sp.K ? maxChunks : 1);
+  B.scIn = cv.take<AutoState>(B.maxSC); B.scLut = cv.take<Lut>(sp.K ? B.maxSC : 1);
+  B.scSum = cv.take<ChunkSum>(B.maxSC); B.scAgg = cv.take<LutAgg>(sp.K ? B.maxSC : 1);
+  B.scBytes = cv.take<uint64_t>(B.maxSC); B.scTok = cv.take<uint32_t>(B.maxSC); B.scBase = cv.take<uint64_t>(B.maxSC);
+  B.scDirty = cv.take<uint8_t>(B.maxSC);
+  B.bigList = cv.take<CopyDesc>((size_t)n / BIG_COPY + 4);
+  return cv.off + 256;
+}
+
+static int dec_top_level(uint32_t inSize)
+{
+  uint64_t g = ((uint64_t)inSize + DEC_B1 - 1) / DEC_B1;
+  int T = 0;
+  while (g > DEC_G && T < DEC_MAX_LEVELS) { g = (g + DEC_G - 1) / DEC_G; T++; }
+  return T;
+}
+
+static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t outSize, void *ws)
+{
+  Carver cv{ (uint8_t *)ws, 0 };
+  D.sp = sp; D.inSize = inSize; D.outSize = outSize;
+  const size_t nC = ((size_t)inSize + DEC_B1 - 1) / DEC_B1;
+  D.sc = cv.take<DecScalars>(1);
+  D.map16 = cv.take<uint16_t>(nC * DEC_B1);
+  D.topLevel = dec_top_level(inSize);
+  for (int l = 0; l <= DEC_MAX_LEVELS; l++) { D.lmap[l] = nullptr; D.lentry[l] = nullptr; }
+  for (int l = 0; l <= D.topLevel; l++)
+  {
+    const uint64_t S = dec_level_bytes(l);
+    const size_t nG = (size_t)(((uint64_t)inSize + S - 1) / S);
+    if (l >= 1) D.lmap[l] = cv.take<uint32_t>(nG * DEC_WIN);
+    D.lentry[l] = cv.take<uint32_t>(nG + DEC_G);
+  }
+  D.cTok = cv.take<uint32_t>(nC + 1); D.cOut = cv.take<uint64_t>(nC + 1);
+  D.cSym = cv.take<uint64_t>(nC + 1); D.cHasSym = cv.take<uint8_t>(nC + 1);
+  D.cXf = cv.take<LutXf>(sp.K ? nC + 1 : 1); D.cLutIn = cv.take<Lut>(sp.K ? nC + 1 : 1);
+  D.maxTok = inSize / 2 + 2;
+  D.tOut = cv.take<uint32_t>((size_t)D.maxTok + 2); D.tLitSrc = cv.take<uint32_t>((size_t)D.maxTok + 2);
+  D.tLitLen = cv.take<uint32_t>((size_t)D.maxTok + 2); D.tSym = cv.take<uint64_t>((size_t)D.maxTok + 2);
+  D.tileFirst = cv.take<uint32_t>((size_t)outSize / DEC_TILE + 4);
+  return cv.off + 256;
+}
+
+static bool spec_from_codec(int codec, Spec &sp)
+{
+  if (codec < 0 || codec >= 48) return false;
+  const int wi = codec >> 3, ba = (codec >> 2) & 1, var = codec & 3;
+  const int W = width_from_index(wi);
+  if (W == 1 && !ba) return false;
+  sp = make_spec(W, ba, var);
+  return true;
+}
+
+static std::mutex g_attrMu;
+static bool g_attrDone[48];
+static bool enc_prepare(int codec, const EncKernels *k)
+{
+  std::lock_guard<std::mutex> lk(g_attrMu);
+  if (g_attrDone[codec]) return true;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->autom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->autoSmem), "attr auto")) return false;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
+  g_attrDone[codec] = true;
+  return true;
+}
+
+static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut, uint32_t cap, void *ws, size_t wsSize, uint32_t *dResult, cudaStream_t st)
+{
+  Spec sp;
+  if (!spec_from_codec(codec, sp) || !dIn || !dOut || !ws || !dResult || n == 0) { g_err = "bad argument"; return 1; }
+  if (((uintptr_t)dIn & 15) || ((uintptr_t)dOut & 15) || ((uintptr_t)ws & 255)) { g_err = "device pointers must be 16-byte aligned (workspace 256)"; return 1; }
+  const EncKernels *k = enc_kernels_for(codec);
+  if (!k) { g_err = "codec not built"; return 1; }
+  if (!enc_prepare(codec, k)) return 2;
+  EncBufs B; memset(&B, 0, sizeof(B));
+  size_t zeroBytes = 0;
+  const size_t need = enc_carve(B, sp, n, ws, &zeroBytes);
+  if (need > wsSize) { g_err = "workspace too small"; return 1; }
+  B.in = dIn; B.out = dOut; B.cap = cap; B.dResult = dResult;
+  if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
+  const int sms = num_sms();
+  HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
+  const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 4);
+  for (int r = 0; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+  HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
+  HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
+  return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
+}
+
+static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize, void *ws, size_t wsSize, uint32_t *dResult, cudaStream_t st)
+{
+  Spec sp;
+  if (!spec_from_codec(codec, sp) || !dIn || !dOut || !ws || !dResult || inSize == 0 || outSize == 0) { g_err = "bad argument"; return 1; }
+  if (((uintptr_t)dIn & 15) || ((uintptr_t)dOut & 15) || ((uintptr_t)ws & 255)) { g_err = "device pointers must be 16-byte aligned (workspace 256)"; return 1; }
+  DecBufs D; memset(&D, 0, sizeof(D));
+  const size_t need = dec_carve(D, sp, inSize, outSize, ws);
+  if (need > wsSize) { g_err = "workspace too small"; return 1; }
+  D.in = dIn; D.out = dOut;
+  const uint32_t nC = (uint32_t)(((uint64_t)inSize + DEC_B1 - 1) / DEC_B1);
+  HSRLE_LAUNCH(k_dec_init, 1, 1, 0, st, D);
+  HSRLE_LAUNCH(k_dec_map, nC, 256, 0, st, D);
+  for (int l = 1; l <= D.topLevel; l++) HSRLE_LAUNCH(k_dec_up, GS_GRID, GS_BLOCK, 0, st, D, l);
+  HSRLE_LAUNCH(k_dec_top, 1, 1, 0, st, D);
+  for (int l = D.topLevel; l >= 1; l--) HSRLE_LAUNCH(k_dec_down, GS_GRID, GS_BLOCK, 0, st, D, l);
+  HSRLE_LAUNCH(k_dec_walk<false>, GS_GRID, GS_BLOCK, 0, st, D);
+  HSRLE_LAUNCH(k_dec_scan, 1, DSCAN_T, 0, st, D, dResult);
+  HSRLE_LAUNCH(k_dec_walk<true>, GS_GRID, GS_BLOCK, 0, st, D);
+  HSRLE_LAUNCH(k_dec_expand, GS_GRID * 2, 256, 0, st, D);
+  return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// library-owned context for the synchronous entry points
+struct Context
+{
+  std::mutex mu;
+  int dev = -1;
+  bool tried = false;
+  cudaStream_t stream = nullptr;
+  void *ws = nullptr; size_t wsSize = 0;
+  uint8_t *dIn = nullptr; size_t dInSize = 0;
+  uint8_t *dOut = nullptr; size_t dOutSize = 0;
+  uint32_t *dResult = nullptr; uint32_t *hResult = nullptr;
+
+  bool init()
+  {
+    if (tried) return dev >= 0;
+    tried = true;
+    int count = 0;
+    if (!cuda_ok(cudaGetDeviceCount(&count), "cudaGetDeviceCount") || count == 0) { if (g_err.empty()) g_err = "no CUDA device"; return false; }
+    int d = 0;
+    if (!cuda_ok(cudaGetDevice(&d), "cudaGetDevice")) return false;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "stream")) return false;
+    if (!cuda_ok(cudaMalloc(&dResult, 64), "malloc result")) return false;
+    if (!cuda_ok(cudaMallocHost(&hResult, 64), "malloc host result")) return false;
+    dev = d;
+    return true;
+  }
+  bool grow(void **p, size_t *cur, size_t need)
+  {
+    if (*cur >= need) return true;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cur = 0;
+    need += need / 8 + 4096;
+    if (!cuda_ok(cudaMalloc(p, need), "cudaMalloc workspace")) return false;
+    *cur = need;
+    return true;
+  }
+};
+static Context g_ctx;
+static void set_func_attrs() {}
+
+static uint32_t run_sync(bool compress, int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
+{
+  Context &C = g_ctx;
+  Spec sp;
+  if (!spec_from_codec(codec, sp)) return 0;
+  EncBufs B; DecBufs D;
+  const size_t need = compress ? enc_carve(B, sp, inSize, nullptr, nullptr) : dec_carve(D, sp, inSize, outSize, nullptr);
+  if (!C.grow(&C.ws, &C.wsSize, need)) return 0;
+  const int rc = compress ? enc_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream)
+                          : dec_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream);
+  if (rc) return 0;
+  if (!cuda_ok(cudaMemcpyAsync(C.hResult, C.dResult, 32, cudaMemcpyDeviceToHost, C.stream), "result copy")) return 0;
+  if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
+  return C.hResult[1] == ST_OK ? C.hResult[0] : 0;
+}
+
+} // namespace hsrle
+
+// ================================================================================================
+// C ABI
+using namespace hsrle;
+
+extern "C" {
+
+uint32_t rle_compress_bounds(const uint32_t inSize)
+{
+  if (inSize > (1u << 30)) return 0;
+  return inSize + (16 + 4 + 1 + 4 + 1 + 64) * 2 + 12 + 1;
+}
+uint32_t rle_decompress_additional_size(void) { return 128; }
+
+int hsrle_codec_id(int symbolBits, int byteAligned, int variant)
+{
+  int wi;
+  switch (symbolBits) { case 8: wi = 0; break; case 16: wi = 1; break; case 24: wi = 2; break; case 32: wi = 3; break; case 48: wi = 4; break; case 64: wi = 5; break; default: return -1; }
+  if (variant < 0 || variant > 3) return -1;
+  if (wi == 0) byteAligned = 1;
+  return wi * 8 + (byteAligned ? 4 : 0) + variant;
+}
+
+int hsrle_codec_id_from_name(const char *name)
+{
+  if (!name) return -1;
+  int bits = 0; const char *p = name;
+  if (strncmp(p, "rle", 3) != 0) return -1;
+  p += 3;
+  while (*p >= '0' && *p <= '9') { bits = bits * 10 + (*p - '0'); p++; }
+  if (*p != '_') return -1;
+  p++;
+  const std::string rest(p);
+  if (bits == 8)
+  {
+    if (rest == "multi" || rest == "") return hsrle_codec_id(8, 1, 0);
+    if (rest == "packed_multi" || rest == "packed") return hsrle_codec_id(8, 1, 1);
+    if (rest == "3symlut") return hsrle_codec_id(8, 1, 2);
+    if (rest == "7symlut") return hsrle_codec_id(8, 1, 3);
+    return -1;
+  }
+  if (rest == "sym") return hsrle_codec_id(bits, 0, 0);
+  if (rest == "byte") return hsrle_codec_id(bits, 1, 0);
+  if (rest == "sym_packed") return hsrle_codec_id(bits, 0, 1);
+  if (rest == "byte_packed") return hsrle_codec_id(bits, 1, 1);
+  if (rest == "3symlut_sym") return hsrle_codec_id(bits, 0, 2);
+  if (rest == "3symlut_byte") return hsrle_codec_id(bits, 1, 2);
+  if (rest == "7symlut_sym") return hsrle_codec_id(bits, 0, 3);
+  if (rest == "7symlut_byte") return hsrle_codec_id(bits, 1, 3);
+  return -1;
+}
+
+size_t hsrle_compress_workspace_size(int codec, uint32_t inSize)
+{
+  Spec sp; if (!spec_from_codec(codec, sp) || inSize == 0) return 0;
+  EncBufs B; return enc_carve(B, sp, inSize, nullptr, nullptr);
+}
+size_t hsrle_decompress_workspace_size(int codec, uint32_t inSize, uint32_t outSize)
+{
+  Spec sp; if (!spec_from_codec(codec, sp) || inSize == 0) return 0;
+  DecBufs D; return dec_carve(D, sp, inSize, outSize, nullptr);
+}
+
+int hsrle_compress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
+                                void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream)
+{
+  set_func_attrs();
+  return enc_enqueue(codec, dIn, inSize, dOut, outSize, dWorkspace, workspaceSize, dResult, (cudaStream_t)cudaStream);
+}
+int hsrle_decompress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
+                                  void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream)
+{
+  set_func_attrs();
+  return dec_enqueue(codec, dIn, inSize, dOut, outSize, dWorkspace, workspaceSize, dResult, (cudaStream_t)cudaStream);
+}
+
+uint32_t hsrle_compress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
+{
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (!g_ctx.init()) return 0;
+  return run_sync(true, codec, dIn, inSize, dOut, outSize);
+}
+uint32_t hsrle_decompress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
+{
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (!g_ctx.init()) return 0;
+  return run_sync(false, codec, dIn, inSize, dOut, outSize);
+}
+
+uint32_t hsrle_compress_host(int codec, const uint8_t *pIn, uint32_t inSize, uint8_t *pOut, uint32_t outSize)
+{
+  // preconditions of the reference: src/rle8_extreme_cpu.h:88, src/rleX_extreme_cpu.h:49, src/rleX_Xsl.h:271
+  if (pIn == NULL || inSize == 0 || pOut == NULL || outSize < rle_compress_bounds(inSize)) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  Context &C = g_ctx;
+  if (!C.init()) return 0;
+  if (!C.grow((void **)&C.dIn, &C.dInSize, (size_t)inSize + 64)) return 0;
+  if (!C.grow((void **)&C.dOut, &C.dOutSize, (size_t)outSize + 64)) return 0;
+  if (!cuda_ok(cudaMemcpyAsync(C.dIn, pIn, inSize, cudaMemcpyHostToDevice, C.stream), "H2D")) return 0;
+  const uint32_t r = run_sync(true, codec, C.dIn, inSize, C.dOut, outSize);
+  if (r == 0) return 0;
+  if (!cuda_ok(cudaMemcpyAsync(pOut, C.dOut, r, cudaMemcpyDeviceToHost, C.stream), "D2H")) return 0;
+  if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
+  return r;
+}
+
+uint32_t hsrle_decompress_host(int codec, const uint8_t *pIn, uint32_t inSize, uint8_t *pOut, uint32_t outSize)
+{
+  if (pIn == NULL || pOut == NULL || inSize == 0 || outSize == 0) return 0;
+  // header check on the host first (src/rle8_extreme_cpu.h:707-712): only the stream itself is uploaded
+  if (inSize < 8) return 0;
+  uint32_t n, clen; memcpy(&n, pIn, 4); memcpy(&clen, pIn + 4, 4);
+  if (n > outSize || clen > inSize || clen < 8) return 0;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  Context &C = g_ctx;
+  if (!C.init()) return 0;
+  if (!C.grow((void **)&C.dIn, &C.dInSize, (size_t)clen + 64)) return 0;
+  if (!C.grow((void **)&C.dOut, &C.dOutSize, (size_t)n + 64)) return 0;
+  if (!cuda_ok(cudaMemcpyAsync(C.dIn, pIn, clen, cudaMemcpyHostToDevice, C.stream), "H2D")) return 0;
+  const uint32_t r = run_sync(false, codec, C.dIn, clen, C.dOut, n);
+  if (r == 0) return 0;
+  if (!cuda_ok(cudaMemcpyAsync(pOut, C.dOut, r, cudaMemcpyDeviceToHost, C.stream), "D2H")) return 0;
+  if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
+  return r;
+}
+
+void hsrle_timing_begin(void)
+{
+  for (auto &t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  g_timed.clear(); g_timing = true;
+}
+// Synchronises the device and writes "kernel:launches:total_ms;..." for every kernel launched since
+// hsrle_timing_begin().  Returns the number of characters written.
+int hsrle_timing_end(char *buf, int bufSize)
+{
+  g_timing = false;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> acc;
+  for (auto &t : g_timed)
+  {
+    float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
+    auto &e = acc[t.name]; e.first++; e.second += ms;
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  g_timed.clear();
+  std::string out;
+  for (auto &kv : acc) { char tmp[256]; snprintf(tmp, sizeof(tmp), "%s:%d:%.6f;", kv.first.c_str(), kv.second.first, kv.second.second); out += tmp; }
+  if (!buf || bufSize <= 0) return 0;
+  const int nw = (int)std::min<size_t>(out.size(), (size_t)bufSize - 1);
+  memcpy(buf, out.data(), nw); buf[nw] = 0;
+  return nw;
+}
+
+const char *hsrle_last_error(void) { return g_err.c_str(); }
+int hsrle_device(void) { std::lock_guard<std::mutex> lk(g_ctx.mu); g_ctx.init(); return g_ctx.dev; }
+uint64_t hsrle_kernel_launches(void) { return g_launches.load(); }
+
+#define HSRLE_PAIR(cname, dname, bits, ba, var)                                                                                   \
+  uint32_t cname(const uint8_t *pIn, const uint32_t inSize, uint8_t *pOut, const uint32_t outSize)                                 \
+  { return hsrle_compress_host(hsrle_codec_id(bits, ba, var), pIn, inSize, pOut, outSize); }                                       \
+  uint32_t dname(const uint8_t *pIn, const uint32_t inSize, uint8_t *pOut, const uint32_t outSize)                                 \
+  { return hsrle_decompress_host(hsrle_codec_id(bits, ba, var), pIn, inSize, pOut, outSize); }
+
+HSRLE_PAIR(rle8_multi_compress, rle8_decompress, 8, 1, 0)
+HSRLE_PAIR(rle8_packed_multi_compress, rle8_packed_decompress, 8, 1, 1)
+HSRLE_PAIR(rle8_3symlut_compress, rle8_3symlut_decompress, 8, 1, 2)
+HSRLE_PAIR(rle8_7symlut_compress, rle8_7symlut_decompress, 8, 1, 3)
+#define HSRLE_WIDTH(bits)                                                                        \
+  HSRLE_PAIR(rle##bits##_sym_compress, rle##bits##_sym_decompress, bits, 0, 0)                   \
+  HSRLE_PAIR(rle##bits##_byte_compress, rle##bits##_byte_decompress, bits, 1, 0)                 \
+  HSRLE_PAIR(rle##bits##_sym_packed_compress, rle##bits##_sym_packed_decompress, bits, 0, 1)     \
+  HSRLE_PAIR(rle##bits##_byte_packed_compress, rle##bits##_byte_packed_decompress, bits, 1, 1)   \
+  HSRLE_PAIR(rle##bits##_3symlut_sym_compress, rle##bits##_3symlut_sym_decompress, bits, 0, 2)   \
+  HSRLE_PAIR(rle##bits##_3symlut_byte_compress, rle##bits##_3symlut_byte_decompress, bits, 1, 2) \
+  HSRLE_PAIR(rle##bits##_7symlut_sym_compress, rle##bits##_7symlut_sym_decompress, bits, 0, 3)   \
+  HSRLE_PAIR(rle##bits##_7symlut_byte_compress, rle##bits##_7symlut_byte_decompress, bits, 1, 3)
+HSRLE_WIDTH(16)
+HSRLE_WIDTH(24)
+HSRLE_WIDTH(32)
+HSRLE_WIDTH(48)
+HSRLE_WIDTH(64)
+
+} // extern "C"

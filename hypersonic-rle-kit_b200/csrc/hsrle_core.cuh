@@ -14,8 +14,10 @@
 
 #ifdef __CUDACC__
 #define HSRLE_HD __host__ __device__ __forceinline__
+#define HSRLE_HDC constexpr __host__ __device__ __forceinline__
 #else
 #define HSRLE_HD inline
+#define HSRLE_HDC constexpr inline
 #endif
 
 namespace hsrle {
@@ -37,9 +39,9 @@ struct Spec
   int RB;         // LUT: range bits in the u16 head (7 / 6)
 };
 
-HSRLE_HD Spec make_spec(int W, int byteAlign, int variant)
+HSRLE_HDC Spec make_spec(int W, int byteAlign, int variant)
 {
-  Spec sp;
+  Spec sp{};
   sp.W = W; sp.byteAlign = (W == 1) ? 1 : byteAlign; sp.variant = variant;
   sp.K = variant == V_LUT3 ? 3 : (variant == V_LUT7 ? 7 : 0);
   sp.hdr = (W == 1 && (variant == V_PLAIN || variant == V_PACKED)) ? 9 : 8;
@@ -85,6 +87,35 @@ struct TokenHdr
   HSRLE_HD void put32(uint32_t v) { put8(v); put8(v >> 8); put8(v >> 16); put8(v >> 24); }
   HSRLE_HD void putsym(uint64_t s, int W) { for (int i = 0; i < W; i++) put8((uint32_t)(s >> (8 * i))); }
 };
+
+// Header byte sinks for enc_eval: CountSink only measures, TokenHdr buffers, PtrSink writes through.
+struct CountSink
+{
+  uint32_t len;
+  HSRLE_HD void put8(uint32_t) { len++; }
+  HSRLE_HD void put16(uint32_t) { len += 2; }
+  HSRLE_HD void put32(uint32_t) { len += 4; }
+  HSRLE_HD void putsym(uint64_t, int W) { len += W; }
+};
+struct PtrSink
+{
+  uint32_t len;
+  uint8_t *p;
+  HSRLE_HD void put8(uint32_t v) { p[len++] = (uint8_t)v; }
+  HSRLE_HD void put16(uint32_t v) { put8(v); put8(v >> 8); }
+  HSRLE_HD void put32(uint32_t v) { put8(v); put8(v >> 8); put8(v >> 16); put8(v >> 24); }
+  HSRLE_HD void putsym(uint64_t s, int W) { for (int i = 0; i < W; i++) put8((uint32_t)(s >> (8 * i))); }
+};
+
+// The W bytes at offset d (0 <= d < W) of the period-W pattern whose first period is sym0.
+HSRLE_HD uint64_t sym_rot(uint64_t sym0, int W, uint32_t d)
+{
+  if (W == 1 || d == 0) return sym0;
+  const int sh = 8 * (int)d;
+  uint64_t r = (sym0 >> sh) | (sym0 << (8 * W - sh));
+  if (W < 8) r &= (1ull << (8 * W)) - 1ull;
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------
 // encoder automaton state
@@ -181,8 +212,10 @@ HSRLE_HD LutAgg lutagg_combine(const LutAgg &older, const LutAgg &newer, int K)
 // Returns EV_* flags.  With EV_EMIT, [s,e) is the run, `h` its header bytes (everything before the
 // literal), and the literal is in[lastBefore, s).  State is advanced either way.
 enum : uint32_t { EV_VALID = 1, EV_EMIT = 2, EV_SYMSET = 4 };
-HSRLE_HD uint32_t enc_eval(const Spec &sp, const uint8_t *in, uint32_t n, uint32_t a, uint32_t b, AutoState &st, Lut &lut, LutAgg *agg,
-                       uint32_t &s, uint32_t &e, TokenHdr &h)
+// `sym0` = the W input bytes in[a-W, a) (the first period of the run the mask run [a,b) belongs to).
+template <class Sink>
+HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a, uint32_t b, AutoState &st, Lut &lut, LutAgg *agg,
+                       uint32_t &s, uint32_t &e, Sink &h)
 {
   const int W = sp.W;
   if (W == 1) { s = a - 1; e = b; }
@@ -195,7 +228,7 @@ HSRLE_HD uint32_t enc_eval(const Spec &sp, const uint8_t *in, uint32_t n, uint32
     st.cursor = e;
   }
   const uint32_t cnt = e - s;
-  const uint64_t sym = load_sym(in + s, W);
+  const uint64_t sym = sym_rot(sym0, W, s - (a - W));
   h.len = 0;
 
   if (sp.K)

@@ -1,0 +1,196 @@
+// hsrle_enc.cuh -- encoder pipeline of the B200 extreme-RLE codec (three phases).
+//
+//   E1  k_enc_scan<W,MINM>   one pass over the input: match mask M[p] = (in[p] == in[p-W]) from coalesced
+//                            16-byte-per-lane loads, run boundaries by bit tricks on 32-bit windows of M,
+//                            compaction of (start, end, first-period symbol) records with a decoupled
+//                            look-back over tiles (single pass, the input is read once).
+//   E2  k_enc_auto<codec>    the reference's per-run emit rules (hsrle_core.cuh: enc_eval) as a speculative
+//                            automaton.  A super-chunk of 2048 records is one CTA: every thread evaluates 16
+//                            records from a warmed-up guess of the incoming state, a block scan of the
+//                            chunk summaries yields the exact incoming states under the current decisions,
+//                            mismatching chunks re-run -- a fixed point of (run -> scan -> compare) is exactly
+//                            the sequential result.  The last CTA to finish scans the super-chunk summaries
+//                            (state, token bytes), marks super-chunks whose guessed incoming state was
+//                            wrong; those re-run in the next round.  After the last round a sequential
+//                            repair (one CTA, still parallel inside a super-chunk) is the exact fallback.
+//   E3  k_enc_emit<codec>    token headers + literal scatter at the scanned stream offsets.
+//       k_enc_copy_big       grid-wide copy of the few very long literals.
+//
+// Reference behaviour restated (never copied): scanners src/rle8_extreme_cpu.h:936-1099,
+// src/rleX_extreme_cpu_encode.h:46-381; emit rules see hsrle_core.cuh.
+#pragma once
+#include "hsrle_core.cuh"
+
+namespace hsrle {
+
+enum : uint32_t { ST_OK = 0, ST_OVERFLOW = 1, ST_BADSTREAM = 2, ST_BADARG = 3 };
+
+// ---------------------------------------------------------------- tunables
+constexpr int E1_T = 256;                 // threads per scan tile
+constexpr int E1_VPT = 4;                 // 16-byte vectors per thread
+constexpr int E1_TILE_VECS = E1_T * E1_VPT;   // 1024 vectors = 16 KiB of input per tile
+constexpr int E2_T = 128;                 // threads per super-chunk CTA
+constexpr int E2_CH = 16;                 // records per thread
+constexpr int E2_SCR = E2_T * E2_CH;      // records per super-chunk
+constexpr int E2_MAXIT = 6;               // in-CTA fixed-point rounds before the in-CTA sequential pass
+constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
+constexpr uint32_t E3_INLINE = 24;        // literals up to this many bytes are copied by the emitting thread
+constexpr uint32_t BIG_COPY = 16384;      // literals at least this long go to the grid-wide copy kernel
+
+// ---------------------------------------------------------------- device-resident bookkeeping
+struct EncScalars
+{
+  uint32_t tileTicket;                    // E1 dynamic tile ids
+  uint32_t nRuns, nSC;
+  uint32_t done[E2_ROUNDS];               // E2 per-round "CTAs finished" counters
+  uint32_t nDirty[E2_ROUNDS];
+  uint32_t firstDirty[E2_ROUNDS];
+  uint32_t status;
+  uint32_t total;                         // final stream size
+  uint32_t nTok;
+  uint32_t nBig;
+  uint32_t serialSC;                      // super-chunks repaired sequentially (diagnostics)
+  uint32_t innerSerial;                   // super-chunks that needed the in-CTA sequential pass (diagnostics)
+  uint64_t tokBytes;                      // sum over tokens of header + literal bytes
+};
+
+struct CopyDesc { uint32_t dst, src, len; };
+
+struct ChunkSum
+{
+  uint32_t flags;       // EV_EMIT: `last` written | EV_VALID: `cursor` written | EV_SYMSET: `lastSym` written
+  uint32_t last, cursor;
+  uint64_t lastSym;
+};
+HSRLE_HD ChunkSum chunksum_identity() { ChunkSum c; c.flags = 0; c.last = 0; c.cursor = 0; c.lastSym = 0; return c; }
+HSRLE_HD void chunksum_apply(AutoState &st, const ChunkSum &c)
+{
+  if (c.flags & EV_EMIT) st.last = c.last;
+  if (c.flags & EV_VALID) st.cursor = c.cursor;
+  if (c.flags & EV_SYMSET) st.lastSym = c.lastSym;
+}
+HSRLE_HD ChunkSum chunksum_combine(const ChunkSum &older, const ChunkSum &newer)
+{
+  ChunkSum r = older;
+  if (newer.flags & EV_EMIT) r.last = newer.last;
+  if (newer.flags & EV_VALID) r.cursor = newer.cursor;
+  if (newer.flags & EV_SYMSET) r.lastSym = newer.lastSym;
+  r.flags |= newer.flags;
+  return r;
+}
+HSRLE_HD AutoState enc_initial_state() { AutoState s; s.cursor = 0; s.last = 0; s.lastSym = 0; return s; }
+
+// scan element: what a segment of records does to the automaton state, plus its token totals
+template <int K> struct SegSum
+{
+  ChunkSum cs;
+  LutAgg agg;           // only meaningful for K > 0
+  uint64_t bytes;
+  uint32_t ntok;
+};
+
+struct EncBufs
+{
+  const uint8_t *in; uint32_t n;
+  uint8_t *out; uint32_t cap;
+  uint32_t nVec, nTiles, lastVec;
+  uint32_t maxRuns, maxSC;
+  unsigned long long *tileStatus;        // E1 look-back: flag(2) | ends(31) | starts(31)
+  uint32_t *runA, *runB; void *runSym;   // records: mask run [a,b), first-period symbol (u32 if W <= 4 else u64)
+  AutoState *cIn; Lut *cLut;             // per 16-record chunk: exact incoming state (written by E2, read by E3)
+  AutoState *scIn; Lut *scLut;           // per super-chunk: assumed incoming state
+  ChunkSum *scSum; LutAgg *scAgg;        // per super-chunk: summary under the current decisions
+  uint64_t *scBytes; uint32_t *scTok;    // per super-chunk: token bytes / tokens
+  uint64_t *scBase;                      // per super-chunk: exclusive token-byte offset
+  uint8_t *scDirty;
+  CopyDesc *bigList;
+  EncScalars *sc;
+  uint32_t *dResult;
+};
+
+// ---------------------------------------------------------------- E1 helpers (host+device)
+// nibble of byte-equality bits of two words
+HSRLE_HD uint32_t eq_nibble(uint32_t x, uint32_t y)
+{
+  const uint32_t t = x ^ y;
+  const uint32_t nz = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t | 0x7F7F7F7Fu);   // 0x80 in every equal byte
+  return (nz * 0x00204081u) >> 28;
+}
+HSRLE_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, s);
+#else
+  return s == 0 ? lo : ((lo >> s) | (hi << (32 - s)));
+#endif
+}
+// c = { bytes -8..-5, -4..-1, 0..3, 4..7, 8..11, 12..15 } relative to the vector start; returns the 16 raw
+// equality bits (in[p] == in[p-W]) of the vector
+template <int W> HSRLE_HD uint32_t m16_raw(const uint32_t *c)
+{
+  uint32_t m = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < 4; j++)
+  {
+    const int off = 8 + 4 * j - W, wi = off >> 2, bs = (off & 3) * 8;
+    const uint32_t y = bs ? funnel_r(c[wi], c[wi + 1], bs) : c[wi];
+    m |= eq_nibble(c[2 + j], y) << (4 * j);
+  }
+  return m;
+}
+// validity: M[p] is defined for W <= p < n only
+template <int W> HSRLE_HD uint32_t m16_valid(uint32_t v, uint32_t n)
+{
+  const uint64_t p0 = (uint64_t)v * 16;
+  if (p0 >= n) return 0;
+  const uint64_t rem = (uint64_t)n - p0;
+  uint32_t m = rem >= 16 ? 0xFFFFu : ((1u << rem) - 1u);
+  if (v == 0) m &= ~((1u << W) - 1u);
+  return m;
+}
+// run boundaries of the 16 positions of a vector from the 32-bit window A (bit i <-> position p0-8+i)
+template <int MINM> HSRLE_HD void m16_boundaries(uint32_t A, uint32_t &starts, uint32_t &ends)
+{
+  uint32_t ones = A;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 1; j < MINM; j++) ones &= (A >> j);
+  const uint32_t s = A & ~(A << 1) & ones;
+  const uint32_t e = ~A & (A << 1) & (ones << MINM);
+  starts = (s >> 8) & 0xFFFFu;
+  ends = (e >> 8) & 0xFFFFu;
+}
+
+// ---------------------------------------------------------------- E2 helpers (host+device)
+template <int K> HSRLE_HD SegSum<K> segsum_identity()
+{
+  SegSum<K> s; s.cs = chunksum_identity(); s.agg.m = 0; s.bytes = 0; s.ntok = 0;
+  return s;
+}
+template <int K> HSRLE_HD SegSum<K> segsum_combine(const SegSum<K> &older, const SegSum<K> &newer)
+{
+  SegSum<K> r;
+  r.cs = chunksum_combine(older.cs, newer.cs);
+  if (K) r.agg = lutagg_combine(older.agg, newer.agg, K); else r.agg.m = 0;
+  r.bytes = older.bytes + newer.bytes; r.ntok = older.ntok + newer.ntok;
+  return r;
+}
+template <int K> HSRLE_HD void segsum_apply(AutoState &st, Lut &lut, const SegSum<K> &s)
+{
+  chunksum_apply(st, s.cs);
+  if (K) lut_apply(lut, K, s.agg);
+}
+
+// state guess for a chunk whose predecessor records are unknown: "a run was just emitted right before
+// the first candidate", initial LUT
+HSRLE_HD void enc_neutral_state(const Spec &sp, uint32_t firstA, AutoState &st, Lut &lut)
+{
+  st = enc_initial_state();
+  st.last = firstA - sp.W;
+  lut_init(lut, sp.W);
+}
+
+} // namespace hsrle
