@@ -96,7 +96,7 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   const size_t maxChunks = (size_t)B.maxSC * E2_T;
   // zero-initialised region first: scalars + look-back status words
   B.sc = cv.take<EncScalars>(1);
-  B.tileStatus = cv.take<unsigned long long>(B.nTiles + 1);
+  B.tileStatus = cv.take<unsigned long long>(2 * (size_t)B.nTiles + 2);
   if (zeroBytes) *zeroBytes = cv.off;
   B.runA = cv.take<uint32_t>(B.maxRuns); B.runB = cv.take<uint32_t>(B.maxRuns);
   B.runSym = cv.take<uint64_t>(sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns);
@@ -106,6 +106,7 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   B.scBytes = cv.take<uint64_t>(B.maxSC); B.scTok = cv.take<uint32_t>(B.maxSC); B.scBase = cv.take<uint64_t>(B.maxSC);
   B.scDirty = cv.take<uint8_t>(B.maxSC);
   B.bigList = cv.take<CopyDesc>((size_t)n / BIG_COPY + 4);
+  B.medList = cv.take<CopyDesc>((size_t)n / MED_COPY + 4);
   return cv.off + 256;
 }
 
@@ -181,7 +182,7 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
-  const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 4);
+  const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
   for (int r = 0; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);

@@ -26,16 +26,18 @@ namespace hsrle {
 enum : uint32_t { ST_OK = 0, ST_OVERFLOW = 1, ST_BADSTREAM = 2, ST_BADARG = 3 };
 
 // ---------------------------------------------------------------- tunables
-constexpr int E1_T = 256;                 // threads per scan tile
-constexpr int E1_VPT = 4;                 // 16-byte vectors per thread
-constexpr int E1_TILE_VECS = E1_T * E1_VPT;   // 1024 vectors = 16 KiB of input per tile
+constexpr int E1_T = 256;                 // threads per scan macro-tile
+constexpr int E1_WARPS = E1_T / 32;
+constexpr int E1_STEPS = 32;              // 512-byte steps per warp (16 KiB contiguous per warp)
+constexpr int E1_TILE_VECS = E1_T * E1_STEPS;   // 8192 vectors = 128 KiB of input per macro-tile
 constexpr int E2_T = 128;                 // threads per super-chunk CTA
-constexpr int E2_CH = 16;                 // records per thread
+constexpr int E2_CH = 4;                  // records per thread
+constexpr int E2_WARM = 12;               // records a thread warms its state guess up on
 constexpr int E2_SCR = E2_T * E2_CH;      // records per super-chunk
 constexpr int E2_MAXIT = 6;               // in-CTA fixed-point rounds before the in-CTA sequential pass
 constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
-constexpr uint32_t E3_INLINE = 24;        // literals up to this many bytes are copied by the emitting thread
-constexpr uint32_t BIG_COPY = 16384;      // literals at least this long go to the grid-wide copy kernel
+constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
+constexpr uint32_t BIG_COPY = 65536;      // ... and these are split over the whole grid
 
 // ---------------------------------------------------------------- device-resident bookkeeping
 struct EncScalars
@@ -48,7 +50,7 @@ struct EncScalars
   uint32_t status;
   uint32_t total;                         // final stream size
   uint32_t nTok;
-  uint32_t nBig;
+  uint32_t nBig, nMed;
   uint32_t serialSC;                      // super-chunks repaired sequentially (diagnostics)
   uint32_t innerSerial;                   // super-chunks that needed the in-CTA sequential pass (diagnostics)
   uint64_t tokBytes;                      // sum over tokens of header + literal bytes
@@ -95,7 +97,7 @@ struct EncBufs
   uint8_t *out; uint32_t cap;
   uint32_t nVec, nTiles, lastVec;
   uint32_t maxRuns, maxSC;
-  unsigned long long *tileStatus;        // E1 look-back: flag(2) | ends(31) | starts(31)
+  unsigned long long *tileStatus;        // E1 look-back: [2t] aggregate, [2t+1] inclusive prefix: flag(1) | ends(31) | starts(31)
   uint32_t *runA, *runB; void *runSym;   // records: mask run [a,b), first-period symbol (u32 if W <= 4 else u64)
   AutoState *cIn; Lut *cLut;             // per 16-record chunk: exact incoming state (written by E2, read by E3)
   AutoState *scIn; Lut *scLut;           // per super-chunk: assumed incoming state
@@ -103,7 +105,7 @@ struct EncBufs
   uint64_t *scBytes; uint32_t *scTok;    // per super-chunk: token bytes / tokens
   uint64_t *scBase;                      // per super-chunk: exclusive token-byte offset
   uint8_t *scDirty;
-  CopyDesc *bigList;
+  CopyDesc *bigList, *medList;
   EncScalars *sc;
   uint32_t *dResult;
 };

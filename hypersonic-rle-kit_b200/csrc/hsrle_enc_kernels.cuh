@@ -38,11 +38,19 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 }
 
 // ================================================================================================
-// E1: candidate scan, single pass
-constexpr unsigned long long TS_AGG = 1ull << 62, TS_INC = 2ull << 62, TS_MASK = (1ull << 62) - 1;
+// E1: candidate scan, single pass.
+//
+// A CTA owns a macro-tile of E1_WARPS x 16 KiB; each warp walks its own contiguous 16 KiB span in 32 steps of
+// 512 bytes (one 16-byte vector per lane, so every warp load is one contiguous 512-byte request).  The
+// equality masks of neighbouring vectors travel by shuffles, so phase A needs no block barrier at all.
+// Offsets: per-step warp totals -> warp scan -> block scan -> ONE look-back per macro-tile in which all
+// 256 threads sum the aggregates of the up-to-255 preceding tiles of the same 256-tile group plus the
+// inclusive prefix published by the last tile of the previous group (no serial chain inside a group).
+constexpr unsigned long long TS_FLAG = 1ull << 63, TS_MASK = (1ull << 62) - 1;
+constexpr int E1_GROUP = 256;
 
-template <int W> __device__ __forceinline__ uint32_t m16_generic(const uint8_t *in, uint32_t n, uint32_t lastVec, int64_t v)
-{ // slow path for the two halo vectors of a tile
+template <int W> __device__ __forceinline__ uint32_t m16_generic(const uint8_t *__restrict__ in, uint32_t n, uint32_t lastVec, int64_t v)
+{ // slow path for the vectors just outside a warp span
   if (v < 0 || v > (int64_t)lastVec + 1) return 0;
   uint32_t c[6] = { 0, 0, 0, 0, 0, 0 };
   if (v >= 1) { const uint2 p = __ldg(reinterpret_cast<const uint2 *>(in + (size_t)v * 16 - 8)); c[0] = p.x; c[1] = p.y; }
@@ -53,10 +61,10 @@ template <int W> __device__ __forceinline__ uint32_t m16_generic(const uint8_t *
 template <int W, int MINM, class SymT>
 __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
 {
-  __shared__ uint16_t mb[E1_TILE_VECS + 2];
-  __shared__ uint32_t warpTot[E1_T / 32];
+  __shared__ uint32_t masks[E1_WARPS][E1_STEPS][32];   // starts | ends << 16 of every vector of the macro-tile
+  __shared__ uint32_t warpTot[E1_WARPS];
+  __shared__ unsigned long long redBuf[E1_WARPS];
   __shared__ uint32_t sTile;
-  __shared__ unsigned long long sBase;
   EncScalars &sc = *B.sc;
   if (threadIdx.x == 0) sTile = atomicAdd(&sc.tileTicket, 1u);
   __syncthreads();
@@ -64,125 +72,167 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
   if (tile >= B.nTiles) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = B.n, lastVec = B.lastVec;
-  const uint4 *in16 = reinterpret_cast<const uint4 *>(B.in);
-  const uint32_t v0 = tile * E1_TILE_VECS + warp * (32 * E1_VPT) + lane;
+  const uint8_t *__restrict__ in = B.in;
+  const uint4 *in16 = reinterpret_cast<const uint4 *>(in);
+  const uint32_t vw = tile * E1_TILE_VECS + warp * (32 * E1_STEPS);   // first vector of this warp's span
 
-  // phase 1: raw equality masks, one 16-byte vector per lane and step (each warp load is 512 contiguous bytes)
-  uint32_t c2 = 0, c3 = 0;   // the 8 bytes before the current warp-step
+  // ---- phase A: masks and per-step totals (no block barrier); loads run one group of 4 steps ahead
+  uint32_t c2 = 0, c3 = 0;                 // the 8 input bytes before the current step
+  if (lane == 0 && vw >= 1 && vw - 1 <= lastVec) { const uint2 p = __ldg(reinterpret_cast<const uint2 *>(in + (size_t)vw * 16 - 8)); c2 = p.x; c3 = p.y; }
+  c2 = __shfl_sync(0xFFFFFFFFu, c2, 0); c3 = __shfl_sync(0xFFFFFFFFu, c3, 0);
+  const uint32_t mBeforeSpan = __shfl_sync(0xFFFFFFFFu, (lane == 0) ? m16_generic<W>(in, n, lastVec, (int64_t)vw - 1) : 0u, 0);
+  const uint32_t mAfterSpan = __shfl_sync(0xFFFFFFFFu, (lane == 0) ? m16_generic<W>(in, n, lastVec, (int64_t)vw + 32 * E1_STEPS) : 0u, 0);
+  uint32_t myStepTot = 0;                  // lane j keeps the total of step j
+  auto finalize = [&](int j, uint32_t prevLast, uint32_t cur, uint32_t nextFirst)
   {
-    const uint32_t vb = v0 - lane;
-    if (lane == 0 && vb >= 1 && vb - 1 <= lastVec) { const uint2 p = __ldg(reinterpret_cast<const uint2 *>(B.in + (size_t)vb * 16 - 8)); c2 = p.x; c3 = p.y; }
-    c2 = __shfl_sync(0xFFFFFFFFu, c2, 0); c3 = __shfl_sync(0xFFFFFFFFu, c3, 0);
-  }
+    uint32_t left = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
+    if (lane == 0) left = prevLast;
+    uint32_t right = __shfl_down_sync(0xFFFFFFFFu, cur, 1);
+    if (lane == 31) right = nextFirst;
+    const uint32_t A = (left >> 8) | (cur << 8) | (right << 24);
+    uint32_t sM, eM;
+    m16_boundaries<MINM>(A, sM, eM);
+    masks[warp][j][lane] = sM | (eM << 16);
+    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(sM) | ((uint32_t)__popc(eM) << 16));
+    if (lane == j) myStepTot = tot;
+  };
+  constexpr int GRP = 4;
+  uint4 buf[GRP];
 #pragma unroll
-  for (int i = 0; i < E1_VPT; i++)
+  for (int k = 0; k < GRP; k++) { const uint32_t v = vw + k * 32 + lane; buf[k] = (v <= lastVec) ? __ldg(in16 + v) : make_uint4(0, 0, 0, 0); }
+  uint32_t pendM = 0, pendPrevLast = mBeforeSpan;
+#pragma unroll
+  for (int g = 0; g < E1_STEPS / GRP; g++)
   {
-    const uint32_t v = v0 + i * 32;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (v <= lastVec) x = __ldg(in16 + v);
-    uint32_t p2 = __shfl_up_sync(0xFFFFFFFFu, x.z, 1), p3 = __shfl_up_sync(0xFFFFFFFFu, x.w, 1);
-    if (lane == 0) { p2 = c2; p3 = c3; }
-    c2 = __shfl_sync(0xFFFFFFFFu, x.z, 31); c3 = __shfl_sync(0xFFFFFFFFu, x.w, 31);
-    const uint32_t c[6] = { p2, p3, x.x, x.y, x.z, x.w };
-    mb[1 + warp * (32 * E1_VPT) + i * 32 + lane] = (uint16_t)(m16_raw<W>(c) & m16_valid<W>(v, n));
-  }
-  if (threadIdx.x == 0) mb[0] = (uint16_t)m16_generic<W>(B.in, n, lastVec, (int64_t)tile * E1_TILE_VECS - 1);
-  if (threadIdx.x == 32) mb[E1_TILE_VECS + 1] = (uint16_t)m16_generic<W>(B.in, n, lastVec, (int64_t)(tile + 1) * E1_TILE_VECS);
-  __syncthreads();
-
-  // phase 2: qualifying run starts / ends of every vector, counts, scan
-  uint32_t sMask[E1_VPT], eMask[E1_VPT], excl[E1_VPT];
-  uint32_t run = 0;   // starts | ends << 16, running over the steps of this warp
+    uint4 nxt[GRP];
+    if (g + 1 < E1_STEPS / GRP)
+    {
 #pragma unroll
-  for (int i = 0; i < E1_VPT; i++)
-  {
-    const int idx = 1 + warp * (32 * E1_VPT) + i * 32 + lane;
-    const uint32_t A = ((uint32_t)mb[idx - 1] >> 8) | ((uint32_t)mb[idx] << 8) | ((uint32_t)mb[idx + 1] << 24);
-    m16_boundaries<MINM>(A, sMask[i], eMask[i]);
-    const uint32_t cnt = __popc(sMask[i]) | (__popc(eMask[i]) << 16);
-    uint32_t inc = cnt;
+      for (int k = 0; k < GRP; k++) { const uint32_t v = vw + ((g + 1) * GRP + k) * 32 + lane; nxt[k] = (v <= lastVec) ? __ldg(in16 + v) : make_uint4(0, 0, 0, 0); }
+    }
+    uint32_t m[GRP];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
-    excl[i] = run + inc - cnt;
-    run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    for (int k = 0; k < GRP; k++)
+    {
+      const uint32_t vs = vw + (g * GRP + k) * 32;     // first vector of the step
+      const uint4 x = buf[k];
+      uint32_t p2 = __shfl_up_sync(0xFFFFFFFFu, x.z, 1), p3 = __shfl_up_sync(0xFFFFFFFFu, x.w, 1);
+      if (lane == 0) { p2 = c2; p3 = c3; }
+      c2 = __shfl_sync(0xFFFFFFFFu, x.z, 31); c3 = __shfl_sync(0xFFFFFFFFu, x.w, 31);
+      const uint32_t c[6] = { p2, p3, x.x, x.y, x.z, x.w };
+      m[k] = m16_raw<W>(c);
+      if (vs == 0 || vs + 32 > lastVec) m[k] &= m16_valid<W>(vs + lane, n);
+    }
+    if (g > 0) finalize(g * GRP - 1, pendPrevLast, pendM, __shfl_sync(0xFFFFFFFFu, m[0], 0));
+    uint32_t pl = (g > 0) ? __shfl_sync(0xFFFFFFFFu, pendM, 31) : mBeforeSpan;
+#pragma unroll
+    for (int k = 0; k + 1 < GRP; k++)
+    {
+      finalize(g * GRP + k, pl, m[k], __shfl_sync(0xFFFFFFFFu, m[k + 1], 0));
+      pl = __shfl_sync(0xFFFFFFFFu, m[k], 31);
+    }
+    pendM = m[GRP - 1]; pendPrevLast = pl;
+    if (g + 1 < E1_STEPS / GRP)
+    {
+#pragma unroll
+      for (int k = 0; k < GRP; k++) buf[k] = nxt[k];
+    }
   }
-  if (lane == 0) warpTot[warp] = run;
+  finalize(E1_STEPS - 1, pendPrevLast, pendM, mAfterSpan);
+  // exclusive scan of the step totals inside the warp
+  uint32_t stepInc = myStepTot;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, stepInc, d); if (lane >= d) stepInc += o; }
+  const uint32_t stepExcl = stepInc - myStepTot;
+  if (lane == 31) warpTot[warp] = stepInc;
   __syncthreads();
   uint32_t warpBase = 0, tileTot = 0;
 #pragma unroll
-  for (int w = 0; w < E1_T / 32; w++) { const uint32_t t = warpTot[w]; if (w < warp) warpBase += t; tileTot += t; }
+  for (int w = 0; w < E1_WARPS; w++) { const uint32_t t = warpTot[w]; if (w < warp) warpBase += t; tileTot += t; }
 
-  // decoupled look-back over tiles (warp 0)
-  if (warp == 0)
+  // ---- one look-back per macro-tile, all threads
+  const unsigned long long agg = (unsigned long long)(tileTot & 0xFFFFu) | ((unsigned long long)(tileTot >> 16) << 31);
+  if (threadIdx.x == 0) st_volatile_u64(B.tileStatus + 2 * (size_t)tile, TS_FLAG | agg);
+  const uint32_t g0 = (tile / E1_GROUP) * E1_GROUP;
+  unsigned long long part = 0;
   {
-    const unsigned long long agg = (unsigned long long)(tileTot & 0xFFFFu) | ((unsigned long long)(tileTot >> 16) << 31);
-    unsigned long long exclusive = 0;
-    if (tile == 0) { if (lane == 0) st_volatile_u64(B.tileStatus + 0, TS_INC | agg); }
+    // thread 0: inclusive prefix of the tile before the group; threads 1..: aggregates of tiles g0 .. tile-1
+    if (threadIdx.x == 0) { if (g0 > 0) { unsigned long long st; do { st = ld_volatile_u64(B.tileStatus + 2 * (size_t)(g0 - 1) + 1); } while (!(st & TS_FLAG)); part = st & TS_MASK; } }
     else
     {
-      if (lane == 0) st_volatile_u64(B.tileStatus + tile, TS_AGG | agg);
-      int64_t base = (int64_t)tile - 1;
-      for (;;)
-      {
-        const int64_t idx = base - lane;
-        unsigned long long st = TS_INC;   // virtual tiles before the first one: inclusive prefix 0
-        if (idx >= 0) { do { st = ld_volatile_u64(B.tileStatus + idx); } while ((st >> 62) == 0); }
-        const uint32_t incMask = __ballot_sync(0xFFFFFFFFu, (st >> 62) == 2);
-        const int firstInc = incMask ? (__ffs(incMask) - 1) : 32;
-        unsigned long long val = (lane <= firstInc) ? (st & TS_MASK) : 0ull;
+      const uint32_t p = g0 + threadIdx.x - 1;
+      if (p < tile) { unsigned long long st; do { st = ld_volatile_u64(B.tileStatus + 2 * (size_t)p); } while (!(st & TS_FLAG)); part = st & TS_MASK; }
+    }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
-        exclusive += val;
-        if (incMask) break;
-        base -= 32;
-      }
-      if (lane == 0) st_volatile_u64(B.tileStatus + tile, TS_INC | (exclusive + agg));
-    }
-    if (lane == 0)
-    {
-      sBase = exclusive;
-      if (tile == B.nTiles - 1)
-      {
-        const unsigned long long tot = exclusive + agg;
-        const uint32_t nS = (uint32_t)(tot & 0x7FFFFFFFull), nE = (uint32_t)(tot >> 31);
-        if (nS != nE || nS > B.maxRuns) { sc.status = ST_BADARG; sc.nRuns = 0; sc.nSC = 0; }
-        else { sc.nRuns = nS; sc.nSC = (nS + E2_SCR - 1) / E2_SCR; }
-      }
-    }
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+    if (lane == 0) redBuf[warp] = part;
   }
   __syncthreads();
-  const unsigned long long base = sBase;
-  const uint32_t baseS = (uint32_t)(base & 0x7FFFFFFFull) + (warpBase & 0xFFFFu);
-  const uint32_t baseE = (uint32_t)(base >> 31) + (warpBase >> 16);
-  SymT *runSym = reinterpret_cast<SymT *>(B.runSym);
+  unsigned long long exclusive = 0;
 #pragma unroll
-  for (int i = 0; i < E1_VPT; i++)
+  for (int w = 0; w < E1_WARPS; w++) exclusive += redBuf[w];
+  if (threadIdx.x == 0)
   {
-    const uint32_t p0 = (v0 + i * 32) * 16u;
-    uint32_t ps = baseS + (excl[i] & 0xFFFFu), pe = baseE + (excl[i] >> 16);
-    uint32_t s = sMask[i], e = eMask[i];
+    st_volatile_u64(B.tileStatus + 2 * (size_t)tile + 1, TS_FLAG | (exclusive + agg));
+    if (tile == B.nTiles - 1)
+    {
+      const unsigned long long tot = exclusive + agg;
+      const uint32_t nS = (uint32_t)(tot & 0x7FFFFFFFull), nE = (uint32_t)(tot >> 31);
+      if (nS != nE || nS > B.maxRuns) { sc.status = ST_BADARG; sc.nRuns = 0; sc.nSC = 0; }
+      else { sc.nRuns = nS; sc.nSC = (nS + E2_SCR - 1) / E2_SCR; }
+    }
+  }
+
+  // ---- phase C: write the records
+  const uint32_t baseS = (uint32_t)(exclusive & 0x7FFFFFFFull) + (warpBase & 0xFFFFu);
+  const uint32_t baseE = (uint32_t)(exclusive >> 31) + (warpBase >> 16);
+  SymT *__restrict__ runSym = reinterpret_cast<SymT *>(B.runSym);
+  uint32_t *__restrict__ runA = B.runA, *__restrict__ runB = B.runB;
+  for (int j = 0; j < E1_STEPS; j++)
+  {
+    const uint32_t stepBase = __shfl_sync(0xFFFFFFFFu, stepExcl, j);
+    const uint32_t stepTot = __shfl_sync(0xFFFFFFFFu, myStepTot, j);
+    if (stepTot == 0) continue;
+    const uint32_t m = masks[warp][j][lane];
+    uint32_t s = m & 0xFFFFu, e = m >> 16;
+    const uint32_t cnt = __popc(s) | (__popc(e) << 16);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+    const uint32_t ex = stepBase + inc - cnt;
+    uint32_t ps = baseS + (ex & 0xFFFFu), pe = baseE + (ex >> 16);
+    const uint32_t p0 = (vw + j * 32 + lane) * 16u;
     while (s)
     {
       const uint32_t a = p0 + (__ffs(s) - 1); s &= s - 1;
-      B.runA[ps] = a;
-      runSym[ps] = (SymT)load_sym(B.in + a - W, W);
+      runA[ps] = a;
+      runSym[ps] = (SymT)load_sym(in + a - W, W);
       ps++;
     }
-    while (e) { B.runB[pe++] = p0 + (__ffs(e) - 1); e &= e - 1; }
+    while (e) { runB[pe++] = p0 + (__ffs(e) - 1); e &= e - 1; }
   }
+}
+
+// literals of MED_COPY bytes or more are copied by the grid-wide k_enc_copy_big: one warp per "medium"
+// literal, the whole grid piece-wise over the few "huge" ones
+__device__ __forceinline__ void enc_push_copy(const EncBufs &B, uint32_t dst, uint32_t src, uint32_t len)
+{
+  CopyDesc d; d.dst = dst; d.src = src; d.len = len;
+  if (len >= BIG_COPY) B.bigList[atomicAdd(&B.sc->nBig, 1u)] = d;
+  else B.medList[atomicAdd(&B.sc->nMed, 1u)] = d;
 }
 
 // ================================================================================================
 // E2: automaton
-// padded record index: one pad slot per 16 records keeps the 16-record-per-thread accesses conflict free
-__device__ __forceinline__ int rec_slot(int j) { return j + (j >> 4); }
+// padded record index: one pad slot per chunk keeps the CH-records-per-thread accesses conflict free
+__device__ __forceinline__ int rec_slot(int j) { return j + j / E2_CH; }
 
 template <int W, int BA, int V, class SymT> struct EncCta
 {
   static constexpr int K = (V == V_LUT3) ? 3 : (V == V_LUT7 ? 7 : 0);
   using Seg = SegSum<K>;
-  static constexpr int NREC = E2_SCR + E2_CH;                 // with the halo chunk
-  static constexpr int NSLOT = NREC + (NREC >> 4) + 1;
+  static constexpr int NREC = E2_SCR + E2_WARM;               // with the warm-up halo
+  static constexpr int NSLOT = NREC + NREC / E2_CH + 1;
 
   struct Smem
   {
@@ -258,29 +308,29 @@ template <int W, int BA, int V, class SymT> struct EncCta
     const uint32_t nRuns = B.sc->nRuns, n = B.n;
     const uint32_t lo = s * E2_SCR;
     const uint32_t cnt = min((uint32_t)E2_SCR, nRuns - lo);
-    const int halo = (s > 0) ? E2_CH : 0;
+    const int halo = (s > 0) ? E2_WARM : 0;
     const SymT *runSym = reinterpret_cast<const SymT *>(B.runSym);
     __syncthreads();   // previous users of the shared arrays are done
-    for (int j = threadIdx.x + (E2_CH - halo); j < E2_CH + (int)cnt; j += E2_T)
+    for (int j = threadIdx.x + (E2_WARM - halo); j < E2_WARM + (int)cnt; j += E2_T)
     {
-      const uint32_t g = lo + j - E2_CH;
+      const uint32_t g = lo + j - E2_WARM;
       const int q = rec_slot(j);
       S.a[q] = B.runA[g]; S.b[q] = B.runB[g]; S.sym[q] = runSym[g];
     }
     __syncthreads();
     const int t = threadIdx.x;
-    const int j0 = E2_CH + t * E2_CH;
-    const int j1 = min(j0 + E2_CH, E2_CH + (int)cnt);
+    const int j0 = E2_WARM + t * E2_CH;
+    const int j1 = min(j0 + E2_CH, E2_WARM + (int)cnt);
     const bool active = j0 < j1;
 
     AutoState stIn; Lut lutIn;
     if (t == 0 && given) { stIn = gSt; lutIn = gLut; }
     else if (t == 0 && s == 0) { stIn = enc_initial_state(); lut_init(lutIn, W); }
     else
-    { // warm up over the previous chunk from the neutral guess
-      const int w0 = j0 - E2_CH;
-      enc_neutral_state(sp, active ? S.a[rec_slot(w0)] : 0u, stIn, lutIn);
-      if (active) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<true>(S, n, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+    { // warm up over the preceding E2_WARM records from the neutral guess
+      const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
+      enc_neutral_state(sp, (active && w0 < j0) ? S.a[rec_slot(w0)] : 0u, stIn, lutIn);
+      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<true>(S, n, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
     }
     Seg mine = segsum_identity<K>();
     if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, j0, j1, st, lut); }
@@ -313,7 +363,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         for (int c = 0; c * E2_CH < (int)cnt; c++)
         {
           S.serSt[c] = st; if (K) S.serLut[K ? c : 0] = lut;
-          const int a0 = E2_CH + c * E2_CH, a1 = min(a0 + E2_CH, E2_CH + (int)cnt);
+          const int a0 = E2_WARM + c * E2_CH, a1 = min(a0 + E2_CH, E2_WARM + (int)cnt);
           (void)eval_range<true>(S, n, a0, a1, st, lut);
         }
         atomicAdd(&B.sc->innerSerial, 1u);
@@ -365,7 +415,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         if (sp.hdr == 9) o[8] = 0;
         const uint32_t pos = (uint32_t)(sp.hdr + tokBytes);
         for (uint32_t k = 0; k < h.len; k++) o[pos + k] = h.b[k];
-        if (L >= BIG_COPY) { CopyDesc d; d.dst = pos + h.len; d.src = fin.last; d.len = L; B.bigList[atomicAdd(&sc.nBig, 1u)] = d; }
+        if (L >= MED_COPY) enc_push_copy(B, pos + h.len, fin.last, L);
         else { fPos = pos + h.len; fLen = L; fOk = 1; }
       }
       else sc.total = 0;
@@ -503,17 +553,29 @@ __device__ __forceinline__ void copy_bytes_warp(uint8_t *dst, const uint8_t *src
 }
 
 constexpr int E3_NDESC = E2_SCR;
+constexpr uint32_t E3_PIECE = 16;         // bytes per flattened literal piece
+constexpr uint32_t E3_STAGE = 32768;      // stream bytes of a super-chunk that can be staged in shared memory
+constexpr uint32_t E3_NPIECE = E3_STAGE / E3_PIECE + E3_NDESC + 8;
 
 template <int W, int BA, int V, class SymT> struct EncEmitSmem
 {
   using C = EncCta<W, BA, V, SymT>;
+  alignas(16) uint8_t stage[E3_STAGE + 32];
   uint32_t a[C::NSLOT], b[C::NSLOT];
   SymT sym[C::NSLOT];
   EmitDesc desc[E3_NDESC];
+  uint32_t pieceOff[E3_NDESC + 1];
+  uint16_t pieceDesc[E3_NPIECE];
   unsigned long long warpTot[E2_T / 32];
+  uint32_t warpTot32[E2_T / 32];
   uint32_t nDesc;
 };
 
+// E3: per super-chunk, (1) token byte counts per thread -> block scan -> stream position of every chunk,
+// (2) token headers and literals are assembled in a shared-memory image of the super-chunk's stream segment
+// (literals gathered as 16-byte pieces, one piece per thread and step, wide source loads), (3) the image is
+// flushed with 16-byte aligned, fully coalesced stores.  Segments that do not fit the stage (long literals)
+// take the direct path: headers straight to the stream, literals >= MED_COPY to the grid-wide copy kernel.
 template <int W, int BA, int V, class SymT>
 __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
 {
@@ -526,7 +588,9 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
   EncScalars &sc = *B.sc;
   if (sc.status != ST_OK) return;
   const uint32_t nSC = sc.nSC, nRuns = sc.nRuns, n = B.n;
-  const SymT *runSym = reinterpret_cast<const SymT *>(B.runSym);
+  const SymT *__restrict__ runSym = reinterpret_cast<const SymT *>(B.runSym);
+  const uint8_t *__restrict__ in = B.in;
+  uint8_t *__restrict__ out = B.out;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (uint32_t s = blockIdx.x; s < nSC; s += gridDim.x)
   {
@@ -563,35 +627,118 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
     if (lane == 31) S.warpTot[warp] = inc;
     __syncthreads();
-    unsigned long long pre = 0;
+    unsigned long long pre = 0, segLen = 0;
 #pragma unroll
-    for (int w = 0; w < E2_T / 32; w++) if (w < warp) pre += S.warpTot[w];
-    uint64_t pos = (uint64_t)sp.hdr + B.scBase[s] + pre + (inc - mine);
-    // pass 2: headers, short literals inline, longer ones to the warp-cooperative list
+    for (int w = 0; w < E2_T / 32; w++) { const unsigned long long x = S.warpTot[w]; if (w < warp) pre += x; segLen += x; }
+    const uint64_t seg0 = (uint64_t)sp.hdr + B.scBase[s];
+    uint64_t pos = seg0 + pre + (inc - mine);
+    const bool staged = segLen <= E3_STAGE;            // uniform
+    const uint32_t shift = (uint32_t)(seg0 & 15);      // keeps stage image and stream equally aligned
+    // pass 2: headers, literal descriptors
     if (active)
     {
       AutoState st = st0; Lut lut = lut0; LutAgg dummy; dummy.m = 0;
       for (int j = j0; j < j1; j++)
       {
         const int q = rec_slot(j);
-        uint32_t rs, re; PtrSink h; h.p = B.out + pos;
+        uint32_t rs, re; PtrSink h;
+        h.p = staged ? (S.stage + shift + (uint32_t)(pos - seg0)) : (out + pos);
         const uint32_t lastBefore = st.last;
         const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &dummy : nullptr, rs, re, h);
         if (!(ev & EV_EMIT)) continue;
         const uint32_t lit = rs - lastBefore;
-        const uint32_t dst = (uint32_t)(pos + h.len);
-        if (lit <= E3_INLINE) { for (uint32_t k = 0; k < lit; k++) B.out[dst + k] = B.in[lastBefore + k]; }
-        else if (lit < BIG_COPY) { const uint32_t slot = atomicAdd(&S.nDesc, 1u); EmitDesc d; d.dst = dst; d.src = lastBefore; d.len = lit; S.desc[slot] = d; }
-        else { CopyDesc d; d.dst = dst; d.src = lastBefore; d.len = lit; B.bigList[atomicAdd(&sc.nBig, 1u)] = d; }
+        if (lit)
+        {
+          if (staged) { EmitDesc d; d.dst = shift + (uint32_t)(pos - seg0) + h.len; d.src = lastBefore; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
+          else if (lit >= MED_COPY) enc_push_copy(B, (uint32_t)(pos + h.len), lastBefore, lit);
+          else { EmitDesc d; d.dst = (uint32_t)(pos + h.len); d.src = lastBefore; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
+        }
         pos += h.len + lit;
       }
     }
     __syncthreads();
+    // flat piece list: exclusive scan of ceil(len/16) over the descriptors (E2_CH per thread)
     const uint32_t nd = S.nDesc;
-    for (uint32_t d = warp; d < nd; d += E2_T / 32)
+    uint32_t loc[E2_CH];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < E2_CH; k++)
     {
-      const EmitDesc e = S.desc[d];
-      copy_bytes_warp(B.out + e.dst, B.in + e.src, e.len, lane);
+      const uint32_t d = t * E2_CH + k;
+      loc[k] = sum;
+      if (d < nd) sum += (S.desc[d].len + E3_PIECE - 1) / E3_PIECE;
+    }
+    uint32_t inc32 = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc32, d); if (lane >= d) inc32 += o; }
+    if (lane == 31) S.warpTot32[warp] = inc32;
+    __syncthreads();
+    uint32_t pre32 = 0, totalPieces = 0;
+#pragma unroll
+    for (int w = 0; w < E2_T / 32; w++) { const uint32_t x = S.warpTot32[w]; if (w < warp) pre32 += x; totalPieces += x; }
+    const uint32_t base32 = pre32 + inc32 - sum;
+#pragma unroll
+    for (int k = 0; k < E2_CH; k++)
+    {
+      const uint32_t d = t * E2_CH + k;
+      if (d < nd)
+      {
+        const uint32_t o = base32 + loc[k], np = (S.desc[d].len + E3_PIECE - 1) / E3_PIECE;
+        S.pieceOff[d] = o;
+        if (staged) for (uint32_t q = 0; q < np; q++) S.pieceDesc[o + q] = (uint16_t)d;
+      }
+    }
+    __syncthreads();
+    if (staged)
+    {
+      for (uint32_t i = t; i < totalPieces; i += E2_T)
+      {
+        const uint32_t a = S.pieceDesc[i];
+        const EmitDesc e = S.desc[a];
+        const uint32_t off = (i - S.pieceOff[a]) * E3_PIECE;
+        const uint32_t len = min(E3_PIECE, e.len - off);
+        const uint8_t *src = in + e.src + off;
+        const uint32_t sb = (uint32_t)((uintptr_t)src & 3);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
+        const uint32_t need = sb + len;             // bytes needed from the aligned word stream
+        uint32_t w[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[k] = ((uint32_t)k * 4 < need) ? __ldg(sw + k) : 0u;
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sb * 8);
+        uint8_t *dst = S.stage + e.dst + off;
+#pragma unroll
+        for (uint32_t k = 0; k < E3_PIECE; k++) if (k < len) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+      }
+      __syncthreads();
+      // flush the image: bytes [shift, shift + segLen) of the stage go to stream bytes [seg0, seg0 + segLen)
+      uint8_t *gbase = out + (seg0 - shift);
+      const uint32_t end = shift + (uint32_t)segLen;
+      const uint32_t headEnd = min(end, 16u);
+      if ((uint32_t)t >= shift && (uint32_t)t < headEnd) gbase[t] = S.stage[t];
+      const uint32_t vEnd = end >> 4;               // full vectors are 1 .. vEnd-1
+      for (uint32_t v = 1 + t; v < vEnd; v += E2_T) reinterpret_cast<uint4 *>(gbase)[v] = reinterpret_cast<const uint4 *>(S.stage)[v];
+      const uint32_t tail0 = max(vEnd << 4, 16u);
+      if (tail0 + t < end) gbase[tail0 + t] = S.stage[tail0 + t];
+    }
+    else
+    {
+      for (uint32_t i = t; i < totalPieces; i += E2_T)
+      {
+        uint32_t a = 0, b = nd - 1;           // largest d with pieceOff[d] <= i
+        while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (S.pieceOff[m] <= i) a = m; else b = m - 1; }
+        const EmitDesc e = S.desc[a];
+        const uint32_t off = (i - S.pieceOff[a]) * E3_PIECE;
+        const uint32_t len = min(E3_PIECE, e.len - off);
+        const uint8_t *__restrict__ src = in + e.src + off;
+        uint8_t *__restrict__ dst = out + e.dst + off;
+        uint8_t tmp[E3_PIECE];
+#pragma unroll
+        for (uint32_t k = 0; k < E3_PIECE; k++) if (k < len) tmp[k] = src[k];
+#pragma unroll
+        for (uint32_t k = 0; k < E3_PIECE; k++) if (k < len) dst[k] = tmp[k];
+      }
     }
   }
 }
@@ -602,8 +749,15 @@ constexpr uint32_t BIG_PIECE = 16384;
 static __global__ void __launch_bounds__(256) k_enc_copy_big(const EncBufs B)
 {
   if (B.sc->status != ST_OK) return;
-  const uint32_t nBig = B.sc->nBig;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nMed = B.sc->nMed;
+  const uint32_t nWarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp; i < nMed; i += nWarps)
+  {
+    const CopyDesc cd = B.medList[i];
+    copy_bytes_warp(B.out + cd.dst, B.in + cd.src, cd.len, lane);
+  }
+  const uint32_t nBig = B.sc->nBig;
   constexpr uint32_t SUB = BIG_PIECE / 8;    // one sub-piece per warp
   for (uint32_t i = 0; i < nBig; i++)
   {
