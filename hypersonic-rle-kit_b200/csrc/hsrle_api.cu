@@ -15,7 +15,7 @@
 #include "../../include/hsrle_b200.h"
 #include "hsrle_dispatch.h"
 #include "hsrle_enc_kernels.cuh"
-#include "hsrle_dec_v1_kernels.cuh"
+#include "hsrle_dec_kernels.cuh"
 
 namespace hsrle {
 
@@ -110,37 +110,37 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   return cv.off + 256;
 }
 
-static int dec_top_level(uint32_t inSize)
+static const DecKernels *dec_kernels_for(int codec)
 {
-  uint64_t g = ((uint64_t)inSize + DEC_B1 - 1) / DEC_B1;
-  int T = 0;
-  while (g > DEC_G && T < DEC_MAX_LEVELS) { g = (g + DEC_G - 1) / DEC_G; T++; }
-  return T;
+  const int wi = codec >> 3;
+  const DecKernels *tab = nullptr;
+  switch (wi)
+  {
+    case 0: tab = dec_kernels_w1(); break; case 1: tab = dec_kernels_w2(); break; case 2: tab = dec_kernels_w3(); break;
+    case 3: tab = dec_kernels_w4(); break; case 4: tab = dec_kernels_w6(); break; case 5: tab = dec_kernels_w8(); break;
+    default: return nullptr;
+  }
+  const DecKernels *k = tab + (codec & 7);
+  return k->map ? k : nullptr;
 }
 
-static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t outSize, void *ws)
+static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t outSize, void *ws, size_t *zeroBytes)
 {
   Carver cv{ (uint8_t *)ws, 0 };
-  D.sp = sp; D.inSize = inSize; D.outSize = outSize;
-  const size_t nC = ((size_t)inSize + DEC_B1 - 1) / DEC_B1;
+  D.inSize = inSize; D.outSize = outSize;
+  D.nSC = (uint32_t)(((uint64_t)inSize + DEC_SCB - 1) / DEC_SCB);
+  D.nSeg = (D.nSC + DEC_SEG - 1) / DEC_SEG;
+  const size_t aggBytes = sp.K ? sizeof(DecAgg<7>) : sizeof(DecAgg<0>);
+  // zero-initialised region first
   D.sc = cv.take<DecScalars>(1);
-  D.map16 = cv.take<uint16_t>(nC * DEC_B1);
-  D.topLevel = dec_top_level(inSize);
-  for (int l = 0; l <= DEC_MAX_LEVELS; l++) { D.lmap[l] = nullptr; D.lentry[l] = nullptr; }
-  for (int l = 0; l <= D.topLevel; l++)
-  {
-    const uint64_t S = dec_level_bytes(l);
-    const size_t nG = (size_t)(((uint64_t)inSize + S - 1) / S);
-    if (l >= 1) D.lmap[l] = cv.take<uint32_t>(nG * DEC_WIN);
-    D.lentry[l] = cv.take<uint32_t>(nG + DEC_G);
-  }
-  D.cTok = cv.take<uint32_t>(nC + 1); D.cOut = cv.take<uint64_t>(nC + 1);
-  D.cSym = cv.take<uint64_t>(nC + 1); D.cHasSym = cv.take<uint8_t>(nC + 1);
-  D.cXf = cv.take<LutXf>(sp.K ? nC + 1 : 1); D.cLutIn = cv.take<Lut>(sp.K ? nC + 1 : 1);
-  D.maxTok = inSize / 2 + 2;
-  D.tOut = cv.take<uint32_t>((size_t)D.maxTok + 2); D.tLitSrc = cv.take<uint32_t>((size_t)D.maxTok + 2);
-  D.tLitLen = cv.take<uint32_t>((size_t)D.maxTok + 2); D.tSym = cv.take<uint64_t>((size_t)D.maxTok + 2);
-  D.tileFirst = cv.take<uint32_t>((size_t)outSize / DEC_TILE + 4);
+  D.ticket = cv.take<uint32_t>(4);
+  D.aggFlag = cv.take<uint32_t>(D.nSC + 1); D.incFlag = cv.take<uint32_t>(D.nSC + 1);
+  if (zeroBytes) *zeroBytes = cv.off;
+  D.map = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
+  D.trail = cv.take<uint32_t>((size_t)D.nSeg * DEC_SEG * DEC_WIN);
+  D.segExit = cv.take<uint32_t>((size_t)D.nSeg * DEC_WIN);
+  D.scEntry = cv.take<uint32_t>(D.nSC + 1);
+  D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);
   return cv.off + 256;
 }
 
@@ -189,25 +189,44 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
 }
 
+static std::mutex g_dattrMu;
+static bool g_dattrDone[48];
+static bool g_composeAttr = false;
+static bool dec_prepare(int codec, const DecKernels *k)
+{
+  std::lock_guard<std::mutex> lk(g_dattrMu);
+  if (!g_composeAttr)
+  {
+    if (!cuda_ok(cudaFuncSetAttribute((const void *)k_dec_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_SEG * DEC_WIN * 4)), "attr compose")) return false;
+    g_composeAttr = true;
+  }
+  if (g_dattrDone[codec]) return true;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->resolveSmem), "attr resolve")) return false;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->expandSmem), "attr expand")) return false;
+  g_dattrDone[codec] = true;
+  return true;
+}
+
 static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize, void *ws, size_t wsSize, uint32_t *dResult, cudaStream_t st)
 {
   Spec sp;
   if (!spec_from_codec(codec, sp) || !dIn || !dOut || !ws || !dResult || inSize == 0 || outSize == 0) { g_err = "bad argument"; return 1; }
   if (((uintptr_t)dIn & 15) || ((uintptr_t)dOut & 15) || ((uintptr_t)ws & 255)) { g_err = "device pointers must be 16-byte aligned (workspace 256)"; return 1; }
+  const DecKernels *k = dec_kernels_for(codec);
+  if (!k) { g_err = "codec not built"; return 1; }
+  if (!dec_prepare(codec, k)) return 2;
   DecBufs D; memset(&D, 0, sizeof(D));
-  const size_t need = dec_carve(D, sp, inSize, outSize, ws);
+  size_t zeroBytes = 0;
+  const size_t need = dec_carve(D, sp, inSize, outSize, ws, &zeroBytes);
   if (need > wsSize) { g_err = "workspace too small"; return 1; }
-  D.in = dIn; D.out = dOut;
-  const uint32_t nC = (uint32_t)(((uint64_t)inSize + DEC_B1 - 1) / DEC_B1);
-  HSRLE_LAUNCH(k_dec_init, 1, 1, 0, st, D);
-  HSRLE_LAUNCH(k_dec_map, nC, 256, 0, st, D);
-  for (int l = 1; l <= D.topLevel; l++) HSRLE_LAUNCH(k_dec_up, GS_GRID, GS_BLOCK, 0, st, D, l);
-  HSRLE_LAUNCH(k_dec_top, 1, 1, 0, st, D);
-  for (int l = D.topLevel; l >= 1; l--) HSRLE_LAUNCH(k_dec_down, GS_GRID, GS_BLOCK, 0, st, D, l);
-  HSRLE_LAUNCH(k_dec_walk<false>, GS_GRID, GS_BLOCK, 0, st, D);
-  HSRLE_LAUNCH(k_dec_scan, 1, DSCAN_T, 0, st, D, dResult);
-  HSRLE_LAUNCH(k_dec_walk<true>, GS_GRID, GS_BLOCK, 0, st, D);
-  HSRLE_LAUNCH(k_dec_expand, GS_GRID * 2, 256, 0, st, D);
+  D.in = dIn; D.out = dOut; D.dResult = dResult;
+  if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
+  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DEC_T, k->mapSmem, st, D);
+  HSRLE_LAUNCH(k_dec_compose, D.nSeg, DEC_WIN, DEC_SEG * DEC_WIN * 4, st, D);
+  HSRLE_LAUNCH_NAMED("k_dec_resolve", k->resolve, 1, D2B_T, k->resolveSmem, st, D);
+  HSRLE_LAUNCH_NAMED("k_dec_expand", k->expand, D.nSC, DEC_T, k->expandSmem, st, D);
+  HSRLE_LAUNCH(k_dec_finish, 1, 1, 0, st, D);
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }
 
@@ -258,7 +277,7 @@ static uint32_t run_sync(bool compress, int codec, const uint8_t *dIn, uint32_t 
   Spec sp;
   if (!spec_from_codec(codec, sp)) return 0;
   EncBufs B; DecBufs D;
-  const size_t need = compress ? enc_carve(B, sp, inSize, nullptr, nullptr) : dec_carve(D, sp, inSize, outSize, nullptr);
+  const size_t need = compress ? enc_carve(B, sp, inSize, nullptr, nullptr) : dec_carve(D, sp, inSize, outSize, nullptr, nullptr);
   if (!C.grow(&C.ws, &C.wsSize, need)) return 0;
   const int rc = compress ? enc_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream)
                           : dec_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream);
@@ -329,7 +348,7 @@ size_t hsrle_compress_workspace_size(int codec, uint32_t inSize)
 size_t hsrle_decompress_workspace_size(int codec, uint32_t inSize, uint32_t outSize)
 {
   Spec sp; if (!spec_from_codec(codec, sp) || inSize == 0) return 0;
-  DecBufs D; return dec_carve(D, sp, inSize, outSize, nullptr);
+  DecBufs D; return dec_carve(D, sp, inSize, outSize, nullptr, nullptr);
 }
 
 int hsrle_compress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,

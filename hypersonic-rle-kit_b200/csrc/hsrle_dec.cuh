@@ -1,0 +1,152 @@
+// hsrle_dec.cuh -- decoder pipeline of the B200 extreme-RLE codec.
+//
+// The stream has no sync markers: token k starts where token k-1 ends.  The decoder finds
+// the token chain speculatively per super-chunk (SC, 16 KiB of stream) and resolves it with a merge:
+//
+//   D1  k_dec_map<codec>     per SC: parse a token at EVERY byte offset; a reverse sweep per 128-byte
+//                            mini-block gives "where does a chain that starts here leave the mini-block";
+//                            hopping mini-block to mini-block from the first DEC_WIN offsets of the SC yields
+//                            the SC's windowed exit map (entry offset -> absolute exit position).
+//   D2a k_dec_compose        per segment of 32 SCs: compose the 32 maps (in shared memory) for every window
+//                            entry; keeps the trail (entry into every SC of the segment per window entry).
+//   D2b k_dec_resolve<codec> one CTA: chain the segment maps from the stream start, then pick every SC's
+//                            true entry from the trails.  Entries that fall outside a window (after a long
+//                            literal) are resolved by walking the tokens of that SC directly (slow path).
+//   D3  k_dec_expand<codec>  per SC: rebuild the mini-block exits, mark the true chain, walk the tokens
+//                            (output sizes, symbol / LUT state), decoupled look-back over SCs for the output
+//                            offset and the incoming symbol state, then expand: one 16-byte aligned output
+//                            vector per thread and step (literal gather / period-W run fill).
+//
+// Reference behaviour restated (never copied): token parse src/rleX_extreme_cpu_decode.h:43-163,
+// src/rleX_Xsl.h:580-784, src/rle8_extreme_cpu.h:1558-1632,2020-2087; header checks
+// src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91.
+#pragma once
+#include "hsrle_core.cuh"
+#include "hsrle_enc.cuh"   // ST_* status codes
+
+namespace hsrle {
+
+constexpr uint32_t DEC_SCB = 16384;       // stream bytes per super-chunk
+constexpr uint32_t DEC_MB = 128;          // mini-block bytes (one thread sweeps one mini-block)
+constexpr int DEC_T = DEC_SCB / DEC_MB;   // 128 threads per SC
+constexpr uint32_t DEC_PAD = 32;          // readable bytes after the SC in shared memory (longest token header)
+constexpr uint32_t DEC_WIN = 512;         // entry window of an SC
+constexpr uint32_t DEC_SEG = 32;          // SCs per segment
+constexpr int DEC_GROUP = DEC_T;          // look-back group (thread 0: inclusive prefix, threads 1..: aggregates)
+constexpr uint32_t DEC_TOKCAP = 1024;     // token records kept in shared memory per expansion pass
+
+constexpr uint32_t POS_END = 0xFFFFFFFFu; // chain reached the terminator
+constexpr uint32_t POS_BAD = 0xFFFFFFFEu; // chain ran into an unparsable position
+constexpr uint32_t POS_MISS = 0xFFFFFFFDu; // chain entered an SC outside its window (resolved by the slow path)
+constexpr uint32_t POS_NONE = 0xFFFFFFFCu; // no token starts in this SC / segment
+constexpr uint32_t POS_SPECIAL = 0xFFFFFFF0u;
+
+// exit codes of the per-position table (u16, relative to the SC start)
+constexpr uint32_t EX_FAR = 0x8000u;      // | offset of the far-jumping token (exit beyond c0 + 0x7FFF)
+constexpr uint32_t EX_END = 0xC000u, EX_BAD = 0xC001u;
+
+struct DecScalars
+{
+  uint32_t n, clen, first, single, status;
+  uint32_t singleSym;
+  uint32_t endSeen;
+  uint32_t nTok;
+};
+
+// net effect of a token sequence on the K-entry LUT (decoder side)
+struct LutXf
+{
+  uint64_t sym[7];
+  int8_t ref[8];        // >=0: incoming entry ref[i]; -1: explicit sym[i]
+};
+HSRLE_HD void lutxf_identity(LutXf &x) { for (int i = 0; i < 7; i++) { x.ref[i] = (int8_t)i; x.sym[i] = 0; } x.ref[7] = 0; }
+HSRLE_HD void lutxf_touch(LutXf &x, int K, int idx, uint64_t sym)
+{ // idx<K: move entry idx to front; idx==K: push explicit symbol
+  if (idx == 0) return;
+  uint64_t s0; int8_t r0;
+  if (idx == K) { s0 = sym; r0 = -1; idx = K - 1; } else { s0 = x.sym[idx]; r0 = x.ref[idx]; }
+  for (int j = idx; j > 0; j--) { x.sym[j] = x.sym[j - 1]; x.ref[j] = x.ref[j - 1]; }
+  x.sym[0] = s0; x.ref[0] = r0;
+}
+HSRLE_HD LutXf lutxf_compose(const LutXf &older, const LutXf &newer, int K)
+{
+  LutXf r; r.ref[7] = 0;
+  for (int i = 0; i < 7; i++) { r.sym[i] = 0; r.ref[i] = (int8_t)i; }
+  for (int i = 0; i < K; i++)
+  {
+    if (newer.ref[i] < 0) { r.sym[i] = newer.sym[i]; r.ref[i] = -1; }
+    else { r.sym[i] = older.sym[newer.ref[i]]; r.ref[i] = older.ref[newer.ref[i]]; }
+  }
+  return r;
+}
+HSRLE_HD void lutxf_apply(const LutXf &x, int K, const Lut &in, Lut &out)
+{
+  for (int i = 0; i < K; i++) out.s[i] = x.ref[i] < 0 ? x.sym[i] : in.s[x.ref[i]];
+}
+
+// what a token sequence contributes to the decoder state: output bytes, token count, symbol register
+template <int K> struct DecAgg
+{
+  uint64_t out;
+  uint32_t ntok;
+  uint32_t has;         // K == 0: the sequence set the symbol register
+  uint64_t sym;
+  LutXf xf;             // K > 0
+};
+template <int K> HSRLE_HD DecAgg<K> decagg_identity()
+{
+  DecAgg<K> a; a.out = 0; a.ntok = 0; a.has = 0; a.sym = 0;
+  if (K) lutxf_identity(a.xf);
+  return a;
+}
+template <int K> HSRLE_HD DecAgg<K> decagg_combine(const DecAgg<K> &older, const DecAgg<K> &newer)
+{
+  DecAgg<K> r;
+  r.out = older.out + newer.out; r.ntok = older.ntok + newer.ntok;
+  if (newer.has) { r.has = 1; r.sym = newer.sym; } else { r.has = older.has; r.sym = older.sym; }
+  if (K) r.xf = lutxf_compose(older.xf, newer.xf, K);
+  return r;
+}
+
+struct DecBufs
+{
+  const uint8_t *in; uint32_t inSize;
+  uint8_t *out; uint32_t outSize;
+  uint32_t nSC, nSeg;
+  uint32_t *map;            // [nSC][DEC_WIN]   windowed exit maps
+  uint32_t *trail;          // [nSeg][DEC_SEG][DEC_WIN]  entry into every SC of a segment per window entry
+  uint32_t *segExit;        // [nSeg][DEC_WIN]
+  uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
+  uint32_t *ticket;         // D3 dynamic SC ids (zero-initialised)
+  uint32_t *aggFlag, *incFlag;   // [nSC] look-back flags (zero-initialised)
+  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>
+  DecScalars *sc;
+  uint32_t *dResult;
+};
+
+// header check -- src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91 (every CTA evaluates it itself)
+HSRLE_HD void dec_header(const Spec &sp, const uint8_t *in, uint32_t inSize, uint32_t outSize, DecScalars &sc)
+{
+  sc.status = ST_OK; sc.single = 0; sc.singleSym = 0; sc.endSeen = 0; sc.nTok = 0; sc.n = 0; sc.clen = 0; sc.first = sp.hdr;
+  if (inSize < (uint32_t)sp.hdr) { sc.status = ST_BADARG; return; }
+  sc.n = load32(in); sc.clen = load32(in + 4);
+  if (sc.n > outSize || sc.clen > inSize || sc.clen < (uint32_t)sp.hdr || sc.clen >= POS_SPECIAL) { sc.status = ST_BADARG; return; }
+  if (sp.hdr == 9)
+  {
+    const uint8_t mode = in[8];
+    if (mode == 1) { if (sc.clen < 10) { sc.status = ST_BADARG; return; } sc.single = 1; sc.singleSym = in[9]; sc.first = 10; }
+    else if (mode != 0) { sc.status = ST_BADARG; return; }
+  }
+}
+
+// low 32 bits of the period-W pattern `sym` read at pattern offset d (0 <= d < W)
+HSRLE_HD uint32_t pattern_word(uint64_t sym, int W, uint32_t d)
+{
+  if (W == 1) return (uint32_t)(sym & 0xFF) * 0x01010101u;
+  uint64_t r = sym_rot(sym, W, d);
+  if (W == 2) return (uint32_t)r | ((uint32_t)r << 16);
+  if (W == 3) return (uint32_t)r | ((uint32_t)r << 24);
+  return (uint32_t)r;
+}
+
+} // namespace hsrle

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hsrle_enc.cuh"
+#include "hsrle_dec.cuh"
 
 namespace hsrle {
 
@@ -16,6 +17,15 @@ struct EncKernels
   int minM;
 };
 
+struct DecKernels
+{
+  void (*map)(const DecBufs);
+  void (*resolve)(const DecBufs);
+  void (*expand)(const DecBufs);
+  size_t mapSmem, resolveSmem, expandSmem;
+  size_t aggBytes;        // sizeof(DecAgg<K>)
+};
+
 // table index = byteAlign*4 + variant (see hsrle_codec_id); entries with scan == nullptr do not exist
 const EncKernels *enc_kernels_w1();
 const EncKernels *enc_kernels_w2();
@@ -23,5 +33,11 @@ const EncKernels *enc_kernels_w3();
 const EncKernels *enc_kernels_w4();
 const EncKernels *enc_kernels_w6();
 const EncKernels *enc_kernels_w8();
+const DecKernels *dec_kernels_w1();
+const DecKernels *dec_kernels_w2();
+const DecKernels *dec_kernels_w3();
+const DecKernels *dec_kernels_w4();
+const DecKernels *dec_kernels_w6();
+const DecKernels *dec_kernels_w8();
 
 } // namespace hsrle

@@ -2,6 +2,7 @@
 #include "hsrle_dispatch.h"
 #include <type_traits>
 #include "hsrle_enc_kernels.cuh"
+#include "hsrle_dec_kernels.cuh"
 
 namespace hsrle {
 
@@ -18,6 +19,20 @@ template <int W, int BA, int V> static EncKernels make_enc_kernels()
   k.emitSmem = sizeof(EncEmitSmem<W, BA, V, SymT>);
   k.symBytes = (int)sizeof(SymT);
   k.minM = sp.minM;
+  return k;
+}
+
+template <int W, int BA, int V> static DecKernels make_dec_kernels()
+{
+  constexpr Spec sp = make_spec(W, BA, V);
+  DecKernels k;
+  k.map = &k_dec_map<W, BA, V>;
+  k.resolve = &k_dec_resolve<W, BA, V>;
+  k.expand = &k_dec_expand<W, BA, V>;
+  k.mapSmem = sizeof(DecScSmem);
+  k.resolveSmem = (size_t)D2B_BATCH * DEC_WIN * 4;
+  k.expandSmem = sizeof(DecExpandSmem<sp.K>);
+  k.aggBytes = sizeof(DecAgg<sp.K>);
   return k;
 }
 
@@ -39,6 +54,26 @@ const EncKernels *HSRLE_CAT(enc_kernels_w, HSRLE_INST_W)()
     }
     tab[4] = make_enc_kernels<W, 1, V_PLAIN>(); tab[5] = make_enc_kernels<W, 1, V_PACKED>();
     tab[6] = make_enc_kernels<W, 1, V_LUT3>(); tab[7] = make_enc_kernels<W, 1, V_LUT7>();
+    init = true;
+  }
+  return tab;
+}
+
+const DecKernels *HSRLE_CAT(dec_kernels_w, HSRLE_INST_W)()
+{
+  static DecKernels tab[8];
+  static bool init = false;
+  if (!init)
+  {
+    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, 0, 0, 0, 0 };
+    constexpr int W = HSRLE_INST_W;
+    if constexpr (W > 1)
+    {
+      tab[0] = make_dec_kernels<W, 0, V_PLAIN>(); tab[1] = make_dec_kernels<W, 0, V_PACKED>();
+      tab[2] = make_dec_kernels<W, 0, V_LUT3>(); tab[3] = make_dec_kernels<W, 0, V_LUT7>();
+    }
+    tab[4] = make_dec_kernels<W, 1, V_PLAIN>(); tab[5] = make_dec_kernels<W, 1, V_PACKED>();
+    tab[6] = make_dec_kernels<W, 1, V_LUT3>(); tab[7] = make_dec_kernels<W, 1, V_LUT7>();
     init = true;
   }
   return tab;

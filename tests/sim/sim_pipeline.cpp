@@ -1,8 +1,10 @@
-// TEST TOOL ONLY -- host-side stage simulator.  Drives the *same* per-item stage functions the CUDA
-// kernels wrap (hypersonic-rle-kit_b200/csrc/hsrle_stages.cuh) from plain loops, so the staged
-// algorithm can be compared with the oracle in a container without a GPU.  Never part of the
-// product library: the product has no CPU path.
-#include "../../hypersonic-rle-kit_b200/csrc/hsrle_stages.cuh"
+// TEST TOOL ONLY -- host-side stage simulator.  Drives the *same* host/device rule functions the CUDA
+// kernels use (hypersonic-rle-kit_b200/csrc/hsrle_core.cuh, hsrle_enc.cuh, hsrle_dec_v1.cuh) from plain loops,
+// reproducing the kernels' staged algorithms (candidate scan -> speculative automaton with scan/verify rounds
+// and sequential repair -> emit; boundary maps -> resolution -> walk -> expansion) so they can be compared
+// with the oracle in a container without a GPU.  Never part of the product library: the product has no CPU path.
+#include "../../hypersonic-rle-kit_b200/csrc/hsrle_enc.cuh"
+#include "../../hypersonic-rle-kit_b200/csrc/hsrle_dec_v1.cuh"
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -13,83 +15,207 @@ static uint32_t g_stats[8];
 
 extern "C" void sim_get_stats(uint32_t *o) { memcpy(o, g_stats, sizeof(g_stats)); }
 
-extern "C" uint32_t sim_compress(int W, int align, int variant, const uint8_t *in, uint32_t n, uint8_t *out, uint32_t cap, int rounds)
+// ---------------------------------------------------------------- E1: candidate scan (k_enc_scan)
+template <int W, int MINM> static void sim_scan(const uint8_t *in, uint32_t n, std::vector<uint32_t> &runA, std::vector<uint32_t> &runB, std::vector<uint64_t> &runSym)
+{
+  const uint32_t nVec = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
+  std::vector<uint32_t> m16(nVec + 2, 0);      // m16[v+1] = mask of vector v
+  for (uint32_t v = 0; v < nVec; v++)
+  {
+    uint32_t c[6];
+    for (int j = 0; j < 6; j++)
+    {
+      uint32_t w = 0;
+      for (int k = 0; k < 4; k++) { const int64_t p = (int64_t)v * 16 - 8 + j * 4 + k; if (p >= 0 && p < (int64_t)n) w |= (uint32_t)in[p] << (8 * k); }
+      c[j] = w;
+    }
+    m16[v + 1] = m16_raw<W>(c) & m16_valid<W>(v, n);
+  }
+  for (uint32_t v = 0; v < nVec; v++)
+  {
+    const uint32_t A = (m16[v] >> 8) | (m16[v + 1] << 8) | (m16[v + 2] << 24);
+    uint32_t s, e;
+    m16_boundaries<MINM>(A, s, e);
+    for (int i = 0; i < 16; i++)
+    {
+      if (s >> i & 1) { const uint32_t a = v * 16 + i; runA.push_back(a); runSym.push_back(load_sym(in + a - W, W)); }
+      if (e >> i & 1) runB.push_back(v * 16 + i);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- E2/E3: automaton + emit (k_enc_auto, k_enc_emit)
+struct SimEnc
+{
+  Spec sp; int K;
+  const uint8_t *in; uint32_t n;
+  std::vector<uint32_t> runA, runB; std::vector<uint64_t> runSym;
+  std::vector<AutoState> cIn; std::vector<Lut> cLut;
+
+  template <class Seg> Seg eval_range(uint32_t j0, uint32_t j1, AutoState &st, Lut &lut, uint8_t *out, uint64_t *pos) const
+  {
+    Seg r; r.cs = chunksum_identity(); r.agg.m = 0; r.bytes = 0; r.ntok = 0;
+    uint32_t fl = 0;
+    for (uint32_t j = j0; j < j1; j++)
+    {
+      uint32_t s, e; TokenHdr h;
+      const uint32_t lastBefore = st.last;
+      const uint32_t ev = enc_eval(sp, runSym[j], n, runA[j], runB[j], st, lut, K ? &r.agg : nullptr, s, e, h);
+      fl |= ev;
+      if (ev & EV_EMIT)
+      {
+        const uint32_t lit = s - lastBefore;
+        if (out) { memcpy(out + *pos, h.b, h.len); memcpy(out + *pos + h.len, in + lastBefore, lit); *pos += h.len + lit; }
+        r.bytes += h.len + lit; r.ntok++;
+      }
+    }
+    r.cs.flags = fl; r.cs.last = st.last; r.cs.cursor = st.cursor; r.cs.lastSym = st.lastSym;
+    return r;
+  }
+};
+
+template <int KK> static uint32_t sim_encode_k(SimEnc &E, uint8_t *out, uint32_t cap, int rounds, int maxit)
+{
+  typedef SegSum<KK> Seg;
+  const Spec &sp = E.sp;
+  const uint32_t nRuns = (uint32_t)E.runB.size();
+  const uint32_t nSC = (nRuns + E2_SCR - 1) / E2_SCR;
+  const uint32_t nChunks = nSC * E2_T;
+  E.cIn.assign(nChunks + 1, enc_initial_state()); E.cLut.resize(nChunks + 1);
+  std::vector<AutoState> scIn(nSC + 1); std::vector<Lut> scLut(nSC + 1);
+  std::vector<Seg> scSum(nSC + 1); std::vector<uint64_t> scBase(nSC + 1); std::vector<uint8_t> scDirty(nSC + 1, 0);
+  uint32_t innerSerial = 0, serialSC = 0;
+
+  auto process = [&](uint32_t s, bool given, const AutoState &gSt, const Lut &gLut) -> Seg
+  {
+    const uint32_t lo = s * E2_SCR, cnt = std::min<uint32_t>(E2_SCR, nRuns - lo);
+    const uint32_t nT = (cnt + E2_CH - 1) / E2_CH;
+    std::vector<AutoState> stIn(nT); std::vector<Lut> lutIn(nT); std::vector<Seg> mine(nT);
+    for (uint32_t t = 0; t < nT; t++)
+    {
+      const uint32_t j0 = lo + t * E2_CH, j1 = std::min(j0 + E2_CH, lo + cnt);
+      if (t == 0 && given) { stIn[t] = gSt; lutIn[t] = gLut; }
+      else if (t == 0 && s == 0) { stIn[t] = enc_initial_state(); lut_init(lutIn[t], sp.W); }
+      else
+      {
+        const uint32_t w0 = (s == 0) ? (uint32_t)std::max<int64_t>((int64_t)j0 - E2_WARM, 0) : j0 - E2_WARM;
+        enc_neutral_state(sp, E.runA[w0], stIn[t], lutIn[t]);
+        AutoState ws = stIn[t]; Lut wl = lutIn[t];
+        (void)E.eval_range<Seg>(w0, j0, ws, wl, nullptr, nullptr);
+        stIn[t] = ws; lutIn[t] = wl;
+      }
+      AutoState st = stIn[t]; Lut lut = lutIn[t];
+      mine[t] = E.eval_range<Seg>(j0, j1, st, lut, nullptr, nullptr);
+    }
+    bool converged = false;
+    for (int it = 0; it < maxit; it++)
+    {
+      std::vector<AutoState> want(nT); std::vector<Lut> wantLut(nT);
+      AutoState run = stIn[0]; Lut runLut = lutIn[0];
+      for (uint32_t t = 0; t < nT; t++) { want[t] = run; wantLut[t] = runLut; segsum_apply<KK>(run, runLut, mine[t]); }
+      bool changed = false;
+      for (uint32_t t = 1; t < nT; t++)
+        if (want[t] != stIn[t] || (KK && !lut_equal(wantLut[t], lutIn[t], KK)))
+        {
+          stIn[t] = want[t]; lutIn[t] = wantLut[t]; changed = true;
+          const uint32_t j0 = lo + t * E2_CH, j1 = std::min(j0 + E2_CH, lo + cnt);
+          AutoState st = stIn[t]; Lut lut = lutIn[t];
+          mine[t] = E.eval_range<Seg>(j0, j1, st, lut, nullptr, nullptr);
+        }
+      if (!changed) { converged = true; break; }
+    }
+    if (!converged)
+    {
+      innerSerial++;
+      AutoState st = stIn[0]; Lut lut = lutIn[0];
+      for (uint32_t t = 0; t < nT; t++)
+      {
+        stIn[t] = st; lutIn[t] = lut;
+        const uint32_t j0 = lo + t * E2_CH, j1 = std::min(j0 + E2_CH, lo + cnt);
+        mine[t] = E.eval_range<Seg>(j0, j1, st, lut, nullptr, nullptr);
+      }
+    }
+    Seg total = segsum_identity<KK>();
+    for (uint32_t t = 0; t < nT; t++) { E.cIn[s * E2_T + t] = stIn[t]; E.cLut[s * E2_T + t] = lutIn[t]; total = segsum_combine<KK>(total, mine[t]); }
+    scSum[s] = total;
+    if (!given) { scIn[s] = stIn[0]; scLut[s] = lutIn[0]; }
+    return total;
+  };
+
+  AutoState d0 = enc_initial_state(); Lut dl; lut_init(dl, sp.W);
+  AutoState fin = d0; Lut finLut = dl; uint64_t tokBytes = 0;
+  bool clean = false;
+  for (int r = 0; r < E2_ROUNDS && !clean; r++)
+  {
+    for (uint32_t s = 0; s < nSC; s++)
+    {
+      if (r == 0) process(s, false, d0, dl);
+      else if (scDirty[s]) { const AutoState g = scIn[s]; const Lut gl = scLut[s]; process(s, true, g, gl); }
+    }
+    // scan_verify
+    AutoState st = d0; Lut lut = dl; uint64_t bytes = 0; uint32_t nd = 0, first = 0xFFFFFFFFu;
+    for (uint32_t s = 0; s < nSC; s++)
+    {
+      bool bad = false;
+      if (scIn[s] != st) { scIn[s] = st; bad = true; }
+      if (KK && !lut_equal(scLut[s], lut, KK)) { scLut[s] = lut; bad = true; }
+      scDirty[s] = bad; if (bad) { if (!nd) first = s; nd++; }
+      scBase[s] = bytes;
+      segsum_apply<KK>(st, lut, scSum[s]); bytes += scSum[s].bytes;
+    }
+    if (r < 3) g_stats[2 + r] = nd;
+    if (nd == 0) { clean = true; fin = st; finLut = lut; tokBytes = bytes; break; }
+    if (r == E2_ROUNDS - 1 || r >= rounds)
+    { // sequential repair
+      AutoState run = scIn[first]; Lut runLut = scLut[first]; uint64_t runBytes = scBase[first];
+      for (uint32_t s = first; s < nSC; s++)
+      {
+        const Seg tot = process(s, true, run, runLut);
+        scIn[s] = run; scLut[s] = runLut; scBase[s] = runBytes; serialSC++;
+        segsum_apply<KK>(run, runLut, tot); runBytes += tot.bytes;
+      }
+      fin = run; finLut = runLut; tokBytes = runBytes; clean = true;
+    }
+  }
+  if (nSC == 0) { fin = d0; tokBytes = 0; }
+  g_stats[0] = innerSerial; g_stats[1] = serialSC; g_stats[7] = nSC;
+  // finish + emit
+  const uint32_t L = E.n - fin.last;
+  TokenHdr th; enc_terminator(sp, L, th);
+  const uint64_t total = (uint64_t)sp.hdr + tokBytes + th.len + L;
+  if (total > cap) return 0;
+  const uint32_t nn = E.n, tt = (uint32_t)total;
+  for (int k = 0; k < 4; k++) { out[k] = (uint8_t)(nn >> (8 * k)); out[4 + k] = (uint8_t)(tt >> (8 * k)); }
+  if (sp.hdr == 9) out[8] = 0;
+  for (uint32_t s = 0; s < nSC; s++)
+  {
+    const uint32_t lo = s * E2_SCR, cnt = std::min<uint32_t>(E2_SCR, nRuns - lo);
+    uint64_t pos = (uint64_t)sp.hdr + scBase[s];
+    for (uint32_t t = 0; t * E2_CH < cnt; t++)
+    {
+      const uint32_t j0 = lo + t * E2_CH, j1 = std::min(j0 + E2_CH, lo + cnt);
+      AutoState st = E.cIn[s * E2_T + t]; Lut lut = E.cLut[s * E2_T + t];
+      (void)E.eval_range<Seg>(j0, j1, st, lut, out, &pos);
+    }
+  }
+  const uint64_t pos = (uint64_t)sp.hdr + tokBytes;
+  memcpy(out + pos, th.b, th.len);
+  memcpy(out + pos + th.len, E.in + fin.last, L);
+  return tt;
+}
+
+extern "C" uint32_t sim_compress(int W, int align, int variant, const uint8_t *in, uint32_t n, uint8_t *out, uint32_t cap, int rounds, int maxit)
 {
   if (!in || !out || n == 0) return 0;
-  EncBufs B; memset(&B, 0, sizeof(B));
-  B.sp = make_spec(W, align, variant);
-  B.in = in; B.n = n; B.out = out; B.cap = cap;
-  B.nVec = (uint32_t)(((uint64_t)n + 1 + ENC_VEC - 1) / ENC_VEC);
-  B.nTiles = (B.nVec + ENC_TILE_VECS - 1) / ENC_TILE_VECS;
-  B.maxRuns = n / (B.sp.minM + 1) + 2;
-  std::vector<uint32_t> tileS(B.nTiles + 1), tileE(B.nTiles + 1), runA(B.maxRuns), runB(B.maxRuns);
-  const uint32_t maxChunks = B.maxRuns / ENC_CH + 2;
-  std::vector<AutoState> sIn(maxChunks); std::vector<ChunkSum> cSum(maxChunks);
-  std::vector<Lut> lutIn(maxChunks);
-  std::vector<LutAgg> lutAgg(maxChunks);
-  std::vector<uint64_t> cBytes(maxChunks); std::vector<uint32_t> cTok(maxChunks); std::vector<uint8_t> dirty(maxChunks);
-  std::vector<CopyDesc> copies(B.maxRuns + 2); std::vector<uint32_t> bigList(B.maxRuns + 2);
-  EncScalars sc; memset(&sc, 0, sizeof(sc));
-  B.tileS = tileS.data(); B.tileE = tileE.data(); B.runA = runA.data(); B.runB = runB.data();
-  B.sIn = sIn.data(); B.cSum = cSum.data(); B.lutIn = lutIn.data(); B.lutAgg = lutAgg.data();
-  B.cBytes = cBytes.data(); B.cTok = cTok.data(); B.dirty = dirty.data(); B.copies = copies.data(); B.bigList = bigList.data(); B.sc = &sc;
-
-  // E1 count + scan + write
-  for (int pass = 0; pass < 2; pass++)
-  {
-    for (uint32_t t = 0; t < B.nTiles; t++)
-    {
-      uint32_t ns = 0, ne = 0;
-      uint32_t bs = pass ? tileS[t] : 0, be = pass ? tileE[t] : 0;
-      for (uint32_t v = t * ENC_TILE_VECS; v < (t + 1) * ENC_TILE_VECS && v < B.nVec; v++)
-      {
-        uint32_t w[12], s, e;
-        mark_load_bytes(in, n, (uint64_t)v * ENC_VEC, w);
-        mark_from_words(B.sp, w, n, (uint64_t)v * ENC_VEC, s, e);
-        if (pass)
-        {
-          for (int i = 0; i < 16; i++) { if (s >> i & 1) runA[bs++] = v * ENC_VEC + i; if (e >> i & 1) runB[be++] = v * ENC_VEC + i; }
-        }
-        ns += __builtin_popcount(s); ne += __builtin_popcount(e);
-      }
-      if (!pass) { tileS[t] = ns; tileE[t] = ne; }
-    }
-    if (!pass)
-    {
-      uint32_t as = 0, ae = 0;
-      for (uint32_t t = 0; t < B.nTiles; t++) { uint32_t s = tileS[t], e = tileE[t]; tileS[t] = as; tileE[t] = ae; as += s; ae += e; }
-      if (as != ae) { fprintf(stderr, "sim: starts %u != ends %u\n", as, ae); return 0; }
-      if (as > B.maxRuns) { fprintf(stderr, "sim: runs %u > max %u\n", as, B.maxRuns); return 0; }
-      sc.nRuns = as; sc.nChunks = (as + ENC_CH - 1) / ENC_CH;
-    }
-  }
-  const uint32_t nC = sc.nChunks;
-  // E2
-  for (uint32_t c = 0; c < nC; c++) enc_stage_auto_init(B, c);
-  Lut lut0; lut_init(lut0, B.sp.W);
-  uint32_t usedRounds = 0, first = 0xFFFFFFFFu;
-  for (int r = 0;; r++)
-  {
-    first = 0xFFFFFFFFu;
-    const uint32_t nd = enc_scan_check_range(B, 0, nC, enc_initial_state(), lut0, first);
-    if (r < 5) g_stats[2 + r] = nd;
-    if (!nd) break;
-    if (r >= rounds) { enc_stage_serial(B, first); break; }
-    usedRounds++;
-    for (uint32_t c = 0; c < nC; c++) enc_stage_rerun(B, c);
-  }
-  g_stats[0] = usedRounds; g_stats[1] = sc.serialChunks; g_stats[7] = nC;
-  // E3
-  uint64_t ab = 0; uint32_t at = 0;
-  for (uint32_t c = 0; c < nC; c++) { uint64_t b = cBytes[c]; uint32_t t = cTok[c]; cBytes[c] = ab; cTok[c] = at; ab += b; at += t; }
-  sc.tokBytes = ab; sc.nTok = at; sc.status = ST_OK;
-  enc_stage_finish(B);
-  if (sc.status != ST_OK) return 0;
-  // E4
-  for (uint32_t c = 0; c < nC; c++) enc_stage_emit(B, c);
-  // E5
-  for (uint32_t i = 0; i <= sc.nTok; i++) memcpy(out + copies[i].dst, in + copies[i].src, copies[i].len);
-  return sc.total;
+  SimEnc E; E.sp = make_spec(W, align, variant); E.K = E.sp.K; E.in = in; E.n = n;
+  memset(g_stats, 0, sizeof(g_stats));
+#define SCAN(w, m) if (W == w && E.sp.minM == m) sim_scan<w, m>(in, n, E.runA, E.runB, E.runSym);
+  SCAN(1, 5) SCAN(1, 2) SCAN(2, 2) SCAN(3, 3) SCAN(4, 4) SCAN(6, 6) SCAN(8, 8)
+#undef SCAN
+  if (E.runA.size() != E.runB.size()) { fprintf(stderr, "sim: starts %zu != ends %zu\n", E.runA.size(), E.runB.size()); return 0; }
+  if (E.K == 3) return sim_encode_k<3>(E, out, cap, rounds, maxit);
+  if (E.K == 7) return sim_encode_k<7>(E, out, cap, rounds, maxit);
+  return sim_encode_k<0>(E, out, cap, rounds, maxit);
 }
 
 extern "C" uint32_t sim_decompress(int W, int align, int variant, const uint8_t *in, uint32_t inSize, uint8_t *out, uint32_t outSize)

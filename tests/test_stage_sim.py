@@ -18,21 +18,23 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 def sim():
     so = os.path.join(SIM_DIR, "libsim.so")
     src = os.path.join(SIM_DIR, "sim_pipeline.cpp")
-    hdrs = [os.path.join(ROOT, "hypersonic-rle-kit_b200", "csrc", h) for h in ("hsrle_core.cuh", "hsrle_stages.cuh")]
+    hdrs = [os.path.join(ROOT, "hypersonic-rle-kit_b200", "csrc", h) for h in ("hsrle_core.cuh", "hsrle_enc.cuh", "hsrle_dec_v1.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     lib.sim_compress.restype = ctypes.c_uint32
-    lib.sim_compress.argtypes = [ctypes.c_int] * 3 + [_u8p, ctypes.c_uint32, _u8p, ctypes.c_uint32, ctypes.c_int]
+    lib.sim_compress.argtypes = [ctypes.c_int] * 3 + [_u8p, ctypes.c_uint32, _u8p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
     lib.sim_decompress.restype = ctypes.c_uint32
     lib.sim_decompress.argtypes = [ctypes.c_int] * 3 + [_u8p, ctypes.c_uint32, _u8p, ctypes.c_uint32]
     return lib
 
 
-def _enc(sim, c, data, rounds=4):
+def _enc(sim, c, data, rounds=3, maxit=6):
+    """rounds: grid-level verify rounds before the sequential repair; maxit: in-CTA fixed-point rounds
+    before the in-CTA sequential pass (0 forces the sequential paths)."""
     out = np.zeros(out_capacity(len(data)), dtype=np.uint8)
-    r = sim.sim_compress(c.W, c.align, c.variant, data.ctypes.data_as(_u8p), len(data), out.ctypes.data_as(_u8p), len(out), rounds)
+    r = sim.sim_compress(c.W, c.align, c.variant, data.ctypes.data_as(_u8p), len(data), out.ctypes.data_as(_u8p), len(out), rounds, maxit)
     return out[:r]
 
 
@@ -64,9 +66,9 @@ def _inputs():
 def test_stage_pipeline_matches_oracle(sim, codec):
     for data in _inputs():
         want = oracle_compress(codec, data)
-        for rounds in (4, 0):   # 0 rounds: everything through the serial fallback
-            got = _enc(sim, codec, data, rounds)
-            assert np.array_equal(got, want), f"{codec.name}: staged encoder differs, n={len(data)} rounds={rounds}"
+        for rounds, maxit in ((3, 6), (0, 6), (3, 0), (0, 1)):   # 0: force the sequential repair / in-CTA sequential pass
+            got = _enc(sim, codec, data, rounds, maxit)
+            assert np.array_equal(got, want), f"{codec.name}: staged encoder differs, n={len(data)} rounds={rounds} maxit={maxit}"
         r, dec = _dec(sim, codec, want, len(data))
         assert r == len(data) and np.array_equal(dec, data), f"{codec.name}: staged decoder differs, n={len(data)}"
 
