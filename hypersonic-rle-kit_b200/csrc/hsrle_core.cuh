@@ -327,7 +327,23 @@ struct Tok
   bool valid;
 };
 
-HSRLE_HD void dec_parse(const Spec &sp, bool single, const uint8_t *p, uint64_t avail, Tok &t)
+// byte readers: plain pointer, or anything with u8(offset)
+struct PtrReader
+{
+  const uint8_t *p;
+  HSRLE_HD uint32_t u8(uint32_t o) const { return p[o]; }
+};
+template <class Rd> HSRLE_HD uint32_t rd16(const Rd &r, uint32_t o) { return r.u8(o) | (r.u8(o + 1) << 8); }
+template <class Rd> HSRLE_HD uint32_t rd32(const Rd &r, uint32_t o) { return r.u8(o) | (r.u8(o + 1) << 8) | (r.u8(o + 2) << 16) | (r.u8(o + 3) << 24); }
+template <class Rd> HSRLE_HD uint64_t rd_sym(const Rd &r, uint32_t o, int W)
+{
+  uint64_t v = 0;
+  for (int i = 0; i < W; i++) v |= (uint64_t)r.u8(o + i) << (8 * i);
+  return v;
+}
+
+template <class Rd>
+HSRLE_HD void dec_parse_rd(const Spec &sp, bool single, const Rd &p, uint64_t avail, Tok &t)
 {
   const int W = sp.W;
   uint32_t ip = 0, cnt, rng;
@@ -337,16 +353,16 @@ HSRLE_HD void dec_parse(const Spec &sp, bool single, const uint8_t *p, uint64_t 
   {
     const int K = sp.K;
     HSRLE_NEED(2);
-    const uint32_t head = load16(p); ip = 2;
+    const uint32_t head = rd16(p, 0); ip = 2;
     const int idx = (int)(head >> (K == 3 ? 14 : 13));
     cnt = (head >> sp.RB) & 0x7F;
     rng = head & ((1u << sp.RB) - 1);
     if (idx == K) { HSRLE_NEED(W); t.symKind = 0; t.symOff = ip; ip += W; }
     else t.symKind = 2 + idx;
-    if (cnt == 1) { HSRLE_NEED(2); cnt = load16(p + ip); ip += 2; }
-    else if (cnt == 0) { HSRLE_NEED(4); cnt = load32(p + ip); ip += 4; }
-    if (rng == 1) { HSRLE_NEED(2); rng = load16(p + ip); ip += 2; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
-    else if (rng == 0) { HSRLE_NEED(4); rng = load32(p + ip); ip += 4; }
+    if (cnt == 1) { HSRLE_NEED(2); cnt = rd16(p, ip); ip += 2; }
+    else if (cnt == 0) { HSRLE_NEED(4); cnt = rd32(p, ip); ip += 4; }
+    if (rng == 1) { HSRLE_NEED(2); rng = rd16(p, ip); ip += 2; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
+    else if (rng == 0) { HSRLE_NEED(4); rng = rd32(p, ip); ip += 4; }
     if (rng < 2) return;
     t.litLen = rng - 2;
     if (cnt == 0) t.last = true;
@@ -357,36 +373,36 @@ HSRLE_HD void dec_parse(const Spec &sp, bool single, const uint8_t *p, uint64_t 
   {
     if (single)
     {
-      HSRLE_NEED(1); cnt = p[ip++];
-      if (cnt == 0) { HSRLE_NEED(4); cnt = load32(p + ip); ip += 4; }
+      HSRLE_NEED(1); cnt = p.u8(ip++);
+      if (cnt == 0) { HSRLE_NEED(4); cnt = rd32(p, ip); ip += 4; }
       t.symKind = 1;
     }
     else if (sp.variant == V_PLAIN)
     {
       HSRLE_NEED(W + 1);
       t.symKind = 0; t.symOff = 0; ip = W;
-      cnt = p[ip++];
-      if (cnt == 0) { HSRLE_NEED(4); cnt = load32(p + ip); ip += 4; }
+      cnt = p.u8(ip++);
+      if (cnt == 0) { HSRLE_NEED(4); cnt = rd32(p, ip); ip += 4; }
     }
     else
     {
       HSRLE_NEED(1);
-      const uint32_t b0 = p[ip++];
+      const uint32_t b0 = p.u8(ip++);
       cnt = b0 & 0x7F;
-      if (cnt == 0) { HSRLE_NEED(4); cnt = load32(p + ip); ip += 4; }
+      if (cnt == 0) { HSRLE_NEED(4); cnt = rd32(p, ip); ip += 4; }
       if (!(b0 & 0x80)) { HSRLE_NEED(W); t.symKind = 0; t.symOff = ip; ip += W; }
       else t.symKind = 1;
     }
     if (sp.rng7 && !single)
     {
       HSRLE_NEED(1);
-      if (p[ip] & 1) { HSRLE_NEED(4); rng = load32(p + ip) >> 1; ip += 4; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
-      else { rng = p[ip++] >> 1; }
+      if (p.u8(ip) & 1) { HSRLE_NEED(4); rng = rd32(p, ip) >> 1; ip += 4; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
+      else { rng = p.u8(ip++) >> 1; }
     }
     else
     {
-      HSRLE_NEED(1); rng = p[ip++];
-      if (rng == 0) { HSRLE_NEED(4); rng = load32(p + ip); ip += 4; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
+      HSRLE_NEED(1); rng = p.u8(ip++);
+      if (rng == 0) { HSRLE_NEED(4); rng = rd32(p, ip); ip += 4; if (rng == 0) { t.last = true; t.hdrLen = ip; t.valid = true; return; } }
     }
     if (rng < 1) return;
     t.litLen = rng - 1;
@@ -399,6 +415,11 @@ HSRLE_HD void dec_parse(const Spec &sp, bool single, const uint8_t *p, uint64_t 
   t.hdrLen = ip;
   if ((uint64_t)ip + t.litLen > avail) return;
   t.valid = true;
+}
+HSRLE_HD void dec_parse(const Spec &sp, bool single, const uint8_t *p, uint64_t avail, Tok &t)
+{
+  PtrReader r; r.p = p;
+  dec_parse_rd(sp, single, r, avail, t);
 }
 
 } // namespace hsrle

@@ -12,10 +12,14 @@
 //   D2b k_dec_resolve<codec> one CTA: chain the segment maps from the stream start, then pick every SC's
 //                            true entry from the trails.  Entries that fall outside a window (after a long
 //                            literal) are resolved by walking the tokens of that SC directly (slow path).
-//   D3  k_dec_expand<codec>  per SC: rebuild the mini-block exits, mark the true chain, walk the tokens
-//                            (output sizes, symbol / LUT state), decoupled look-back over SCs for the output
-//                            offset and the incoming symbol state, then expand: one 16-byte aligned output
-//                            vector per thread and step (literal gather / period-W run fill).
+//   D3a k_dec_walk<codec>    per SC: mark the true chain (entry into every mini-block, hopping through D1's
+//                            exit table), walk the tokens of every mini-block in parallel: output bytes, token
+//                            count, symbol / LUT state transform of the SC.
+//   D3s k_dec_scan           one CTA: exclusive scan of the SC aggregates (output offset, incoming symbol
+//                            state); final validation (terminator seen, total == uncompressedLength).
+//   D3b k_dec_expand<codec>  per SC: token records (output offset, literal source, run symbol), then one
+//                            16-byte aligned output vector per thread and step (literal gather / period-W
+//                            run fill).
 //
 // Reference behaviour restated (never copied): token parse src/rleX_extreme_cpu_decode.h:43-163,
 // src/rleX_Xsl.h:580-784, src/rle8_extreme_cpu.h:1558-1632,2020-2087; header checks
@@ -113,13 +117,13 @@ struct DecBufs
   const uint8_t *in; uint32_t inSize;
   uint8_t *out; uint32_t outSize;
   uint32_t nSC, nSeg;
+  uint16_t *exTab;          // [nSC][DEC_SCB]   per-position exit tables (D1 -> D3)
   uint32_t *map;            // [nSC][DEC_WIN]   windowed exit maps
   uint32_t *trail;          // [nSeg][DEC_SEG][DEC_WIN]  entry into every SC of a segment per window entry
   uint32_t *segExit;        // [nSeg][DEC_WIN]
   uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
-  uint32_t *ticket;         // D3 dynamic SC ids (zero-initialised)
-  uint32_t *aggFlag, *incFlag;   // [nSC] look-back flags (zero-initialised)
-  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>
+  uint16_t *mbEntry;        // [nSC][DEC_T] entry of the true chain into every mini-block (0xFFFF: none)
+  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals, exclusive prefixes
   DecScalars *sc;
   uint32_t *dResult;
 };

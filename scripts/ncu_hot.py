@@ -13,7 +13,7 @@ for l in lines:
         cur = [l]
     elif cur: cur.append(l)
 if cur: blocks.append(cur)
-b = blocks[int(sys.argv[4]) if len(sys.argv) > 4 else 0]
+b = blocks[min(int(sys.argv[4]) if len(sys.argv) > 4 else 0, len(blocks) - 1)] if blocks else sys.exit("no such kernel")
 print(b[0][:200])
 rows = list(csv.reader(io.StringIO("\n".join(b[1:]))))
 hdr = rows[0]
