@@ -136,9 +136,9 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   if (zeroBytes) *zeroBytes = cv.off;
   D.mbEntry = cv.take<uint16_t>((size_t)D.nSC * DEC_T);
   D.exTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
-  D.map = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
-  D.trail = cv.take<uint32_t>((size_t)D.nSeg * DEC_SEG * DEC_WIN);
-  D.segExit = cv.take<uint32_t>((size_t)D.nSeg * DEC_WIN);
+  D.finTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
+  D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
+  D.segEntry = cv.take<uint32_t>(D.nSeg + 1);
   D.scEntry = cv.take<uint32_t>(D.nSC + 1);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);
   return cv.off + 256;
@@ -202,7 +202,6 @@ static bool dec_prepare(int codec, const DecKernels *k)
   }
   if (g_dattrDone[codec]) return true;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
-  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->resolveSmem), "attr resolve")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->walkSmem), "attr walk")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->expandSmem), "attr expand")) return false;
   g_dattrDone[codec] = true;
@@ -225,7 +224,7 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DEC_T, k->mapSmem, st, D);
   HSRLE_LAUNCH(k_dec_compose, D.nSeg, DEC_WIN, DEC_SEG * DEC_WIN * 4, st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_resolve", k->resolve, 1, D2B_T, k->resolveSmem, st, D);
+  HSRLE_LAUNCH(k_dec_resolve, 1, D2B_T, 0, st, D);
   HSRLE_LAUNCH_NAMED("k_dec_walk", k->walk, D.nSC, DEC_T, k->walkSmem, st, D);
   HSRLE_LAUNCH_NAMED("k_dec_scan", k->scan, 1, D3S_T, 0, st, D);
   HSRLE_LAUNCH_NAMED("k_dec_expand", k->expand, D.nSC, DEC_T, k->expandSmem, st, D);

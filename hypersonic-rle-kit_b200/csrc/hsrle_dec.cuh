@@ -4,14 +4,18 @@
 // the token chain speculatively per super-chunk (SC, 16 KiB of stream) and resolves it with a merge:
 //
 //   D1  k_dec_map<codec>     per SC: parse a token at EVERY byte offset; a reverse sweep per 128-byte
-//                            mini-block gives "where does a chain that starts here leave the mini-block";
-//                            hopping mini-block to mini-block from the first DEC_WIN offsets of the SC yields
-//                            the SC's windowed exit map (entry offset -> absolute exit position).
-//   D2a k_dec_compose        per segment of 32 SCs: compose the 32 maps (in shared memory) for every window
-//                            entry; keeps the trail (entry into every SC of the segment per window entry).
-//   D2b k_dec_resolve<codec> one CTA: chain the segment maps from the stream start, then pick every SC's
-//                            true entry from the trails.  Entries that fall outside a window (after a long
-//                            literal) are resolved by walking the tokens of that SC directly (slow path).
+//                            mini-block gives "where does a chain that starts here leave the mini-block"
+//                            (exTab, kept for D3); a two-level in-place finalisation (warp-blocks, then the
+//                            SC) turns that into "where does it leave the SC" for every offset (finTab,
+//                            absolute positions).  The first DEC_WIN entries of an SC's finTab row are its
+//                            windowed exit map: token chains re-enter the next SC within a few hundred
+//                            bytes of its start unless a long literal spans the boundary.
+//   D2a k_dec_compose        per segment of DEC_SEG SCs, in reverse SC order: sufExit[c][w] = where the chain
+//                            that enters SC c at window offset w leaves the SEGMENT.  Chains that enter an SC
+//                            beyond its window (after a long literal) take one finTab look-up instead.
+//   D2b k_dec_resolve        one CTA: thread 0 chains the segments from the stream start (one look-up per
+//                            segment, one more per long-literal entry), then one thread per segment walks
+//                            its SCs forward through finTab and records every SC's true entry.
 //   D3a k_dec_walk<codec>    per SC: mark the true chain (entry into every mini-block, hopping through D1's
 //                            exit table), walk the tokens of every mini-block in parallel: output bytes, token
 //                            count, symbol / LUT state transform of the SC.
@@ -117,10 +121,10 @@ struct DecBufs
   const uint8_t *in; uint32_t inSize;
   uint8_t *out; uint32_t outSize;
   uint32_t nSC, nSeg;
-  uint16_t *exTab;          // [nSC][DEC_SCB]   per-position exit tables (D1 -> D3)
-  uint32_t *map;            // [nSC][DEC_WIN]   windowed exit maps
-  uint32_t *trail;          // [nSeg][DEC_SEG][DEC_WIN]  entry into every SC of a segment per window entry
-  uint32_t *segExit;        // [nSeg][DEC_WIN]
+  uint16_t *exTab;          // [nSC][DEC_SCB]   per-position mini-block exit tables (D1 -> D3)
+  uint32_t *finTab;         // [nSC][DEC_SCB]   per-position SC exits, absolute (index = stream position)
+  uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
+  uint32_t *segEntry;       // [nSeg] true entry into the segment or POS_NONE
   uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
   uint16_t *mbEntry;        // [nSC][DEC_T] entry of the true chain into every mini-block (0xFFFF: none)
   void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals, exclusive prefixes

@@ -192,12 +192,13 @@ __device__ __forceinline__ uint32_t dec_code_to_pos(const uint8_t *data, uint32_
 }
 
 // ================================================================================================
-// D1: per-position exit tables (kept for D3) and windowed exit maps
+// D1: per-position exit tables: mini-block level (exTab, for D3) and SC level (finTab, for D2)
 struct DecMapSmem
 {
   alignas(16) uint8_t data[DEC_DATA_BYTES];
   alignas(16) uint16_t ex[DEC_EX_ELEMS];
 };
+constexpr uint32_t DEC_WB = 32 * DEC_MB;    // warp-block: the 32 mini-blocks swept by one warp
 
 template <int W, int BA, int V>
 __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
@@ -210,141 +211,120 @@ __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
   if (hs.status != ST_OK) return;
   const uint32_t c = blockIdx.x;
   const uint32_t c0 = c * DEC_SCB;
-  if (c0 >= hs.clen)
-  {
-    for (uint32_t w = threadIdx.x; w < DEC_WIN; w += DEC_T) D.map[(size_t)c * DEC_WIN + w] = POS_BAD;
-    return;
-  }
+  if (c0 >= hs.clen) return;
   const bool single = hs.single != 0;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   dec_load_sc(S.data, D.in, c0, hs.clen);
   __syncthreads();
   dec_sweep<W, BA, V>(S.data, S.ex, c0, hs.clen, single);
   __syncthreads();
-  // keep the table for D3 (two entries per 4-byte store)
+  // keep the mini-block table for D3 (two entries per 4-byte store)
   {
     uint32_t *dst = reinterpret_cast<uint32_t *>(D.exTab + (size_t)c * DEC_SCB);
-    for (uint32_t q = threadIdx.x * 2; q < DEC_SCB; q += DEC_T * 2) dst[q >> 1] = *reinterpret_cast<const uint32_t *>(S.ex + skew16(q));
+    for (uint32_t q = t * 2; q < DEC_SCB; q += DEC_T * 2) dst[q >> 1] = *reinterpret_cast<const uint32_t *>(S.ex + skew16(q));
   }
-  // hop mini-block to mini-block from every window entry
-  for (uint32_t w = threadIdx.x; w < DEC_WIN; w += DEC_T)
+  __syncthreads();
+  // finalise in place, level 1: inside every warp-block, mini-blocks in reverse order (a code below the end of
+  // the warp-block points into a later mini-block of the same warp-block, which is final already)
   {
-    uint32_t code = S.ex[skew16(w)];
-    while (code < DEC_SCB) code = S.ex[skew16(code)];
-    D.map[(size_t)c * DEC_WIN + w] = dec_code_to_pos<W, BA, V>(S.data, code, c0, hs.clen, single);
+    const uint32_t wb0 = warp * DEC_WB, wb1 = wb0 + DEC_WB;
+    for (int mb = 30; mb >= 0; mb--)
+    {
+      uint32_t code[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) code[k] = S.ex[skew16(wb0 + mb * DEC_MB + lane + 32 * k)];
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = S.ex[skew16(code[k])];
+#pragma unroll
+      for (int k = 0; k < 4; k++) S.ex[skew16(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
+      __syncwarp();
+    }
   }
+  __syncthreads();
+  // level 2: warp-blocks in reverse order
+  for (int wb = DEC_T / 32 - 2; wb >= 0; wb--)
+  {
+    for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DEC_T)
+    {
+      uint32_t code = S.ex[skew16(p)];
+      if (code < DEC_SCB) { code = S.ex[skew16(code)]; S.ex[skew16(p)] = (uint16_t)code; }
+    }
+    __syncthreads();
+  }
+  // absolute SC exits of every position
+  uint32_t *fin = D.finTab + (size_t)c * DEC_SCB;
+  for (uint32_t p = t; p < DEC_SCB; p += DEC_T) fin[p] = dec_code_to_pos<W, BA, V>(S.data, S.ex[skew16(p)], c0, hs.clen, single);
 }
 
 // ================================================================================================
-// D2a: compose the maps of one segment
+// D2a: per segment, where does the chain that enters SC c at window offset w leave the segment
 static __global__ void __launch_bounds__(DEC_WIN) k_dec_compose(const DecBufs D)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  uint32_t *maps = reinterpret_cast<uint32_t *>(smemRaw);   // [DEC_SEG][DEC_WIN]
+  uint32_t *suf = reinterpret_cast<uint32_t *>(smemRaw);   // [DEC_SEG][DEC_WIN]
   const DecScalars &sc = *D.sc;
   if (sc.status != ST_OK) return;
+  const uint32_t nSC = (sc.clen + DEC_SCB - 1) / DEC_SCB;
   const uint32_t g = blockIdx.x;
   const uint32_t cFirst = g * DEC_SEG;
-  const uint32_t nHere = min(DEC_SEG, D.nSC - cFirst);
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(D.map + (size_t)cFirst * DEC_WIN);
-    uint4 *dst = reinterpret_cast<uint4 *>(maps);
-    for (uint32_t v = threadIdx.x; v < nHere * DEC_WIN / 4; v += blockDim.x) dst[v] = src[v];
-  }
-  __syncthreads();
+  if (cFirst >= nSC) return;
+  const uint32_t nHere = min(DEC_SEG, nSC - cFirst);
+  const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_SCB;
+  const uint32_t *__restrict__ fin = D.finTab;
   const uint32_t w = threadIdx.x;
-  uint32_t pos = cFirst * DEC_SCB + w;
-  uint32_t *trail = D.trail + (size_t)g * DEC_SEG * DEC_WIN;
-  for (uint32_t i = 0; i < nHere; i++)
+  for (int i = (int)nHere - 1; i >= 0; i--)
   {
-    const uint32_t c0 = (cFirst + i) * DEC_SCB;
-    uint32_t tr = POS_NONE;
-    if (pos < POS_SPECIAL && pos - c0 < DEC_SCB)
+    uint32_t x = fin[(size_t)(cFirst + i) * DEC_SCB + w];
+    while (x < POS_SPECIAL && (uint64_t)x < segEnd)
     {
-      tr = pos;
-      const uint32_t off = pos - c0;
-      pos = off < DEC_WIN ? maps[i * DEC_WIN + off] : POS_MISS;
+      const uint32_t c2 = x / DEC_SCB, off = x - c2 * DEC_SCB;
+      if (off < DEC_WIN) { x = suf[(c2 - cFirst) * DEC_WIN + off]; break; }   // a later SC of the segment: final already
+      x = fin[x];                                                             // entry beyond the window: one SC at a time
     }
-    trail[i * DEC_WIN + w] = tr;
+    suf[i * DEC_WIN + w] = x;
+    __syncthreads();
   }
-  D.segExit[(size_t)g * DEC_WIN + w] = pos;
+  uint32_t *dst = D.sufExit + (size_t)cFirst * DEC_WIN;
+  for (uint32_t i = 0; i < nHere; i++) dst[i * DEC_WIN + w] = suf[i * DEC_WIN + w];
 }
 
 // ================================================================================================
-// D2b: chain the segments, pick the true entries
+// D2b: chain the segments, record the true entry of every SC
 constexpr int D2B_T = 1024;
-constexpr uint32_t D2B_BATCH = 48;        // segment maps staged in shared memory at a time (96 KiB)
 
-template <int W, int BA, int V>
-__device__ uint32_t dec_walk_global(const DecBufs &D, const DecScalars &sc, uint32_t pos, uint32_t end)
-{ // slow path: walk tokens in global memory from pos until the chain leaves [.., end)
-  constexpr Spec sp = make_spec(W, BA, V);
-  while (pos < end)
-  {
-    Tok t; dec_parse(sp, sc.single != 0, D.in + pos, (uint64_t)sc.clen - pos, t);
-    if (!t.valid) return POS_BAD;
-    if (t.last) return POS_END;
-    pos = (uint32_t)((uint64_t)pos + t.hdrLen + t.litLen);
-  }
-  return pos;
-}
-
-template <int W, int BA, int V>
-__global__ void __launch_bounds__(D2B_T) k_dec_resolve(const DecBufs D)
+static __global__ void __launch_bounds__(D2B_T) k_dec_resolve(const DecBufs D)
 {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  uint32_t *segMaps = reinterpret_cast<uint32_t *>(smemRaw);     // [D2B_BATCH][DEC_WIN]
-  __shared__ uint32_t segW[D2B_BATCH];                           // window entry of the true chain per segment / POS_NONE / POS_MISS
-  __shared__ uint32_t sPos;
-  const DecScalars &sc = *D.sc;
+  DecScalars &sc = *D.sc;
   if (sc.status != ST_OK) return;
   const uint32_t clen = sc.clen;
-  if (threadIdx.x == 0) sPos = sc.first;
+  const uint32_t nSC = (clen + DEC_SCB - 1) / DEC_SCB;
+  const uint32_t nSeg = (nSC + DEC_SEG - 1) / DEC_SEG;
+  const uint32_t *__restrict__ fin = D.finTab;
+  for (uint32_t c = threadIdx.x; c < D.nSC; c += blockDim.x) D.scEntry[c] = POS_NONE;
+  for (uint32_t g = threadIdx.x; g < nSeg; g += blockDim.x) D.segEntry[g] = POS_NONE;
   __syncthreads();
-  for (uint32_t gb = 0; gb < D.nSeg; gb += D2B_BATCH)
+  if (threadIdx.x == 0)
   {
-    const uint32_t nb = min(D2B_BATCH, D.nSeg - gb);
+    uint32_t pos = sc.first, lastSeg = 0xFFFFFFFFu;
+    while (pos < POS_SPECIAL)
     {
-      const uint4 *src = reinterpret_cast<const uint4 *>(D.segExit + (size_t)gb * DEC_WIN);
-      uint4 *dst = reinterpret_cast<uint4 *>(segMaps);
-      for (uint32_t v = threadIdx.x; v < nb * DEC_WIN / 4; v += blockDim.x) dst[v] = src[v];
+      if (pos >= clen) { pos = POS_BAD; break; }
+      const uint32_t c = pos / DEC_SCB, g = c / DEC_SEG, off = pos - c * DEC_SCB;
+      if (g != lastSeg) { D.segEntry[g] = pos; lastSeg = g; }
+      pos = off < DEC_WIN ? D.sufExit[(size_t)c * DEC_WIN + off] : fin[pos];
     }
-    __syncthreads();
-    if (threadIdx.x == 0)
+    if (pos != POS_END) sc.status = ST_BADSTREAM;
+  }
+  __syncthreads();
+  for (uint32_t g = threadIdx.x; g < nSeg; g += blockDim.x)
+  {
+    uint32_t pos = D.segEntry[g];
+    const uint64_t segEnd = (uint64_t)(g + 1) * DEC_SEG * DEC_SCB;
+    while (pos < POS_SPECIAL && (uint64_t)pos < segEnd && pos < clen)
     {
-      uint32_t pos = sPos;
-      for (uint32_t k = 0; k < nb; k++)
-      {
-        const uint32_t g = gb + k;
-        const uint32_t s0 = g * DEC_SEG * DEC_SCB;
-        const uint64_t s1 = (uint64_t)s0 + (uint64_t)DEC_SEG * DEC_SCB;
-        if (pos >= POS_SPECIAL || pos >= s1) { segW[k] = POS_NONE; continue; }
-        const uint32_t w = pos - s0;
-        uint32_t e = w < DEC_WIN ? segMaps[k * DEC_WIN + w] : POS_MISS;
-        if (e != POS_MISS) { segW[k] = w; pos = e; continue; }
-        // slow path: SC by SC through this segment
-        segW[k] = POS_MISS;
-        for (uint32_t i = 0; i < DEC_SEG && g * DEC_SEG + i < D.nSC; i++)
-        {
-          const uint32_t c = g * DEC_SEG + i;
-          const uint32_t c0 = c * DEC_SCB;
-          const uint32_t c1 = (uint32_t)min((uint64_t)c0 + DEC_SCB, (uint64_t)clen);
-          if (pos >= POS_SPECIAL || pos - c0 >= DEC_SCB) { D.scEntry[c] = POS_NONE; continue; }
-          D.scEntry[c] = pos;
-          const uint32_t off = pos - c0;
-          pos = off < DEC_WIN ? D.map[(size_t)c * DEC_WIN + off] : dec_walk_global<W, BA, V>(D, sc, pos, c1);
-        }
-      }
-      sPos = pos;
+      D.scEntry[pos / DEC_SCB] = pos;
+      pos = fin[pos];
     }
-    __syncthreads();
-    for (uint32_t c = gb * DEC_SEG + threadIdx.x; c < min(D.nSC, (gb + nb) * DEC_SEG); c += blockDim.x)
-    {
-      const uint32_t k = c / DEC_SEG - gb, i = c % DEC_SEG;
-      const uint32_t w = segW[k];
-      if (w == POS_MISS) continue;
-      D.scEntry[c] = (w == POS_NONE) ? POS_NONE : D.trail[((size_t)(gb + k) * DEC_SEG + i) * DEC_WIN + w];
-    }
-    __syncthreads();
   }
 }
 

@@ -20,11 +20,10 @@ struct EncKernels
 struct DecKernels
 {
   void (*map)(const DecBufs);
-  void (*resolve)(const DecBufs);
   void (*walk)(const DecBufs);
   void (*scan)(const DecBufs);
   void (*expand)(const DecBufs);
-  size_t mapSmem, resolveSmem, walkSmem, expandSmem;
+  size_t mapSmem, walkSmem, expandSmem;
   size_t aggBytes;        // sizeof(DecAgg<K>)
 };
 

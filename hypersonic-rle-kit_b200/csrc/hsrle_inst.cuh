@@ -27,13 +27,11 @@ template <int W, int BA, int V> static DecKernels make_dec_kernels()
   constexpr Spec sp = make_spec(W, BA, V);
   DecKernels k;
   k.map = &k_dec_map<W, BA, V>;
-  k.resolve = &k_dec_resolve<W, BA, V>;
   k.walk = &k_dec_walk<W, BA, V>;
   k.scan = &k_dec_scan<sp.K>;
   k.expand = &k_dec_expand<W, BA, V>;
   k.walkSmem = sizeof(DecWalkSmem<sp.K>);
   k.mapSmem = sizeof(DecMapSmem);
-  k.resolveSmem = (size_t)D2B_BATCH * DEC_WIN * 4;
   k.expandSmem = sizeof(DecExpandSmem<sp.K>);
   k.aggBytes = sizeof(DecAgg<sp.K>);
   return k;
@@ -68,7 +66,7 @@ const DecKernels *HSRLE_CAT(dec_kernels_w, HSRLE_INST_W)()
   static bool init = false;
   if (!init)
   {
-    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0 };
     constexpr int W = HSRLE_INST_W;
     if constexpr (W > 1)
     {

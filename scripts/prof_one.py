@@ -36,6 +36,15 @@ if what in ("dec", "both"):
         hs.decompress_device_async(name, t_out, r, t_dec, n, ws, res[8:], sp)
 ev[2].record()
 torch.cuda.synchronize()
-print(name, "n", n, "clen", r, "enc us", 1e3 * ev[0].elapsed_time(ev[1]) / reps, "dec us", 1e3 * ev[1].elapsed_time(ev[2]) / reps, "res", res.tolist())
+import ctypes
+buf = ctypes.create_string_buffer(8192)
+hs.lib.hsrle_timing_begin()
+if what in ("enc", "both"):
+    hs.compress_device_async(name, t_in[1], t_out, ws, res[:8], sp)
+if what in ("dec", "both"):
+    hs.decompress_device_async(name, t_out, r, t_dec, n, ws, res[8:], sp)
+hs.lib.hsrle_timing_end(buf, 8192)
+kt = " ".join(f"{p.split(':')[0][2:]}={1e3*float(p.split(':')[2]):.0f}" for p in buf.value.decode().split(";") if p)
+print(name, "n", n, "clen", r, "enc us", 1e3 * ev[0].elapsed_time(ev[1]) / reps, "dec us", 1e3 * ev[1].elapsed_time(ev[2]) / reps, "| kernel us:", kt, "| res", res.tolist())
 if what in ("dec", "both"):
     assert torch.equal(t_dec[:n], t_in[0])
