@@ -44,10 +44,17 @@ class ClockSampler:
 
     def __init__(self, gpu):
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -55,21 +62,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 - 0.02 <= ts <= (self.t1 or ts) + 0.04]
+        window = "timed region"
+        if len(rows) < 2:     # a very short timed region: fall back to everything since the sampler started (warm-up included)
+            rows, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        sm = sorted(int(float(r[1])) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -211,6 +223,9 @@ def run_gpu_arm(args):
         r = t_res[c].cpu().numpy()
         assert r[1] == 0 and r[0] > 0 and r[8] == n and r[9] == 0, (c, r)
         csize[c] = int(r[0])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for w in range(max(args.warmup, 3)):
         enqueue_step(w)
     torch.cuda.synchronize()
@@ -221,17 +236,16 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = hs.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for k in range(args.steps):
         enqueue_step(k)
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = hs.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -292,17 +306,14 @@ def run_gpu_arm(args):
     top = max(kt.items(), key=lambda kv: kv[1][1])
     peak, peak_src = peaks()
     csum = sum(csize.values())
-    # algorithmic bytes of the dominant kernel per launch: bytes it must move
-    alg = {"k_enc_count": n, "k_enc_write": n, "k_dec_expand": None, "k_dec_map": None}
+    # algorithmic bytes of the dominant kernel per launch (DESIGN.md, section "Kernels"): the codec bytes that kernel has
+    # to move once -- N = uncompressed bytes, C = mean compressed bytes over the codec set
+    cavg = csum / len(CODEC_SET)
+    alg = {"k_enc_scan": n, "k_enc_auto": None, "k_enc_emit": 2 * cavg, "k_enc_copy_big": None,
+           "k_dec_map": cavg, "k_dec_compose": None, "k_dec_resolve": None, "k_dec_walk": cavg, "k_dec_scan": None,
+           "k_dec_expand": n + cavg}
     name = top[0]
-    if name in ("k_enc_count", "k_enc_write"):
-        alg_bytes = float(n)
-    elif name == "k_dec_expand":
-        alg_bytes = float(n) + csum / len(CODEC_SET)
-    elif name == "k_dec_map":
-        alg_bytes = csum / len(CODEC_SET)
-    else:
-        alg_bytes = float(n) + csum / len(CODEC_SET)
+    alg_bytes = float(alg.get(name) or (n + cavg))     # state-only kernels are charged the whole call (N + C)
     avg_ms = top[1][1] / top[1][0]
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -356,7 +367,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

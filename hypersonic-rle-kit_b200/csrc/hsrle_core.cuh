@@ -20,6 +20,12 @@
 #define HSRLE_HDC constexpr inline
 #endif
 
+#ifdef __CUDA_ARCH__
+#define HSRLE_UNROLL _Pragma("unroll")
+#else
+#define HSRLE_UNROLL
+#endif
+
 namespace hsrle {
 
 enum : int { V_PLAIN = 0, V_PACKED = 1, V_LUT3 = 2, V_LUT7 = 3 };
@@ -132,7 +138,13 @@ struct Lut
 {
   uint64_t s[7];
 };
-HSRLE_HD bool lut_equal(const Lut &a, const Lut &b, int K) { for (int i = 0; i < K; i++) if (a.s[i] != b.s[i]) return false; return true; }
+HSRLE_HD bool lut_equal(const Lut &a, const Lut &b, int K)
+{
+  bool eq = true;
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++) if (i < K) eq = eq && (a.s[i] == b.s[i]);
+  return eq;
+}
 
 HSRLE_HD uint64_t broadcast_byte(uint32_t v, int W)
 {
@@ -148,20 +160,31 @@ HSRLE_HD void lut_init(Lut &l, int W)
   l.s[6] = broadcast_byte(0xFE, W);
 }
 
+// All LUT helpers index their arrays with compile-time constants only (fully unrolled, predicated), so that
+// the tables live in registers on the device; K is a compile-time constant at every call site.
 HSRLE_HD int lut_find(const Lut &l, int K, uint64_t sym)
 {
-  int idx = 0;
-  for (; idx < K; idx++) if (l.s[idx] == sym) break;
+  int idx = K;
+  HSRLE_UNROLL
+  for (int i = 6; i >= 0; i--) if (i < K && l.s[i] == sym) idx = i;
   return idx;
 }
 
-// move-to-front: idx==K pushes a new symbol (dropping the last entry)
+// move-to-front: idx<K moves entry idx (== sym) to the front; idx==K pushes a new symbol (dropping the last entry)
 HSRLE_HD void lut_touch(Lut &l, int K, int idx, uint64_t sym)
 {
-  if (idx == 0) return;
   const int from = idx == K ? K - 1 : idx;
-  for (int j = from; j > 0; j--) l.s[j] = l.s[j - 1];
+  HSRLE_UNROLL
+  for (int j = 6; j > 0; j--) if (j < K && j <= from) l.s[j] = l.s[j - 1];
   l.s[0] = sym;
+}
+// entry idx (< K) of the table
+HSRLE_HD uint64_t lut_get(const Lut &l, int K, int idx)
+{
+  uint64_t v = l.s[0];
+  HSRLE_UNROLL
+  for (int i = 1; i < 7; i++) if (i < K && i == idx) v = l.s[i];
+  return v;
 }
 
 // "K most recent distinct emitted symbols" aggregate of a segment; composition is associative.
@@ -172,10 +195,12 @@ struct LutAgg
 };
 HSRLE_HD void lutagg_push(LutAgg &a, int K, uint64_t sym)
 {
-  int idx = 0;
-  for (; idx < (int)a.m; idx++) if (a.s[idx] == sym) break;
+  int idx = (int)a.m;
+  HSRLE_UNROLL
+  for (int i = 6; i >= 0; i--) if (i < K && i < (int)a.m && a.s[i] == sym) idx = i;
   if (idx == (int)a.m) { if ((int)a.m < K) a.m++; else idx = K - 1; }
-  for (int j = idx; j > 0; j--) a.s[j] = a.s[j - 1];
+  HSRLE_UNROLL
+  for (int j = 6; j > 0; j--) if (j < K && j <= idx) a.s[j] = a.s[j - 1];
   a.s[0] = sym;
 }
 // apply a segment aggregate (newer) on top of a full LUT (older): newer symbols first, then the
@@ -184,25 +209,47 @@ HSRLE_HD void lut_apply(Lut &l, int K, const LutAgg &a)
 {
   if (a.m == 0) return;
   Lut r;
-  int k = 0;
-  for (; k < (int)a.m; k++) r.s[k] = a.s[k];
-  for (int i = 0; i < K && k < K; i++)
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++) r.s[i] = a.s[i];
+  int k = (int)a.m;
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
   {
-    bool dup = false;
-    for (int j = 0; j < (int)a.m; j++) dup |= (a.s[j] == l.s[i]);
-    if (!dup) r.s[k++] = l.s[i];
+    if (i < K)
+    {
+      bool dup = false;
+      HSRLE_UNROLL
+      for (int j = 0; j < 7; j++) if (j < K) dup |= (j < (int)a.m && a.s[j] == l.s[i]);
+      if (!dup && k < K)
+      {
+        HSRLE_UNROLL
+        for (int q = 0; q < 7; q++) if (q < K && q == k) r.s[q] = l.s[i];
+        k++;
+      }
+    }
   }
-  for (int i = 0; i < K; i++) l.s[i] = r.s[i];
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++) if (i < K) l.s[i] = r.s[i];
 }
 // older then newer -> combined aggregate
 HSRLE_HD LutAgg lutagg_combine(const LutAgg &older, const LutAgg &newer, int K)
 {
   LutAgg r = newer;
-  for (int i = 0; i < (int)older.m && (int)r.m < K; i++)
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
   {
-    bool dup = false;
-    for (int j = 0; j < (int)newer.m; j++) dup |= (newer.s[j] == older.s[i]);
-    if (!dup) r.s[r.m++] = older.s[i];
+    if (i < K && i < (int)older.m)
+    {
+      bool dup = false;
+      HSRLE_UNROLL
+      for (int j = 0; j < 7; j++) if (j < K) dup |= (j < (int)newer.m && newer.s[j] == older.s[i]);
+      if (!dup && (int)r.m < K)
+      {
+        HSRLE_UNROLL
+        for (int q = 0; q < 7; q++) if (q < K && q == (int)r.m) r.s[q] = older.s[i];
+        r.m++;
+      }
+    }
   }
   return r;
 }

@@ -67,29 +67,60 @@ struct LutXf
   uint64_t sym[7];
   int8_t ref[8];        // >=0: incoming entry ref[i]; -1: explicit sym[i]
 };
-HSRLE_HD void lutxf_identity(LutXf &x) { for (int i = 0; i < 7; i++) { x.ref[i] = (int8_t)i; x.sym[i] = 0; } x.ref[7] = 0; }
+HSRLE_HD void lutxf_identity(LutXf &x)
+{
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++) { x.ref[i] = (int8_t)i; x.sym[i] = 0; }
+  x.ref[7] = 0;
+}
+// (static indices only: see the LUT helpers in hsrle_core.cuh)
 HSRLE_HD void lutxf_touch(LutXf &x, int K, int idx, uint64_t sym)
 { // idx<K: move entry idx to front; idx==K: push explicit symbol
   if (idx == 0) return;
-  uint64_t s0; int8_t r0;
-  if (idx == K) { s0 = sym; r0 = -1; idx = K - 1; } else { s0 = x.sym[idx]; r0 = x.ref[idx]; }
-  for (int j = idx; j > 0; j--) { x.sym[j] = x.sym[j - 1]; x.ref[j] = x.ref[j - 1]; }
+  uint64_t s0 = sym; int8_t r0 = -1;
+  int from = K - 1;
+  if (idx != K)
+  {
+    from = idx;
+    HSRLE_UNROLL
+    for (int i = 1; i < 7; i++) if (i < K && i == idx) { s0 = x.sym[i]; r0 = x.ref[i]; }
+  }
+  HSRLE_UNROLL
+  for (int j = 6; j > 0; j--) if (j < K && j <= from) { x.sym[j] = x.sym[j - 1]; x.ref[j] = x.ref[j - 1]; }
   x.sym[0] = s0; x.ref[0] = r0;
 }
 HSRLE_HD LutXf lutxf_compose(const LutXf &older, const LutXf &newer, int K)
 {
   LutXf r; r.ref[7] = 0;
-  for (int i = 0; i < 7; i++) { r.sym[i] = 0; r.ref[i] = (int8_t)i; }
-  for (int i = 0; i < K; i++)
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
   {
-    if (newer.ref[i] < 0) { r.sym[i] = newer.sym[i]; r.ref[i] = -1; }
-    else { r.sym[i] = older.sym[newer.ref[i]]; r.ref[i] = older.ref[newer.ref[i]]; }
+    r.sym[i] = 0; r.ref[i] = (int8_t)i;
+    if (i < K)
+    {
+      if (newer.ref[i] < 0) { r.sym[i] = newer.sym[i]; r.ref[i] = -1; }
+      else
+      {
+        HSRLE_UNROLL
+        for (int j = 0; j < 7; j++) if (j < K && newer.ref[i] == j) { r.sym[i] = older.sym[j]; r.ref[i] = older.ref[j]; }
+      }
+    }
   }
   return r;
 }
 HSRLE_HD void lutxf_apply(const LutXf &x, int K, const Lut &in, Lut &out)
 {
-  for (int i = 0; i < K; i++) out.s[i] = x.ref[i] < 0 ? x.sym[i] : in.s[x.ref[i]];
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
+  {
+    if (i < K)
+    {
+      uint64_t v = x.sym[i];
+      HSRLE_UNROLL
+      for (int j = 0; j < 7; j++) if (j < K && x.ref[i] == j) v = in.s[j];
+      out.s[i] = v;
+    }
+  }
 }
 
 // what a token sequence contributes to the decoder state: output bytes, token count, symbol register

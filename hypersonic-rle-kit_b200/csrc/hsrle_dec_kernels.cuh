@@ -499,7 +499,7 @@ __device__ __forceinline__ uint64_t dec_token_symbol(const Tok &t, const SkewRea
   {
     const int idx = t.symKind == 0 ? K : t.symKind - 2;
     if (idx == K) lut_touch(lut, K, K, rd_sym(rd, t.symOff, W));
-    else if (idx > 0) { const uint64_t v = lut.s[idx]; lut_touch(lut, K, idx, v); }
+    else if (idx > 0) { const uint64_t v = lut_get(lut, K, idx); lut_touch(lut, K, idx, v); }
     return lut.s[0];
   }
   if (t.symKind == 0) symReg = rd_sym(rd, t.symOff, W);

@@ -34,8 +34,8 @@ constexpr int E2_T = 128;                 // threads per super-chunk CTA
 constexpr int E2_CH = 4;                  // records per thread
 constexpr int E2_WARM = 12;               // records a thread warms its state guess up on
 constexpr int E2_SCR = E2_T * E2_CH;      // records per super-chunk
-constexpr int E2_MAXIT = 6;               // in-CTA fixed-point rounds before the in-CTA sequential pass
-constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
+constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
+constexpr int E2_ROUNDS = 5;              // grid-level rounds (the last one ends with the sequential repair)
 constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
 constexpr uint32_t BIG_COPY = 65536;      // ... and these are split over the whole grid
 

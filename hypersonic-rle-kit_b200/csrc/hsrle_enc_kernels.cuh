@@ -421,7 +421,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       else sc.total = 0;
       uint32_t *r = B.dResult;
       r[0] = sc.status == ST_OK ? sc.total : 0; r[1] = sc.status; r[2] = sc.nRuns; r[3] = sc.nSC;
-      r[4] = sc.serialSC; r[5] = sc.innerSerial; r[6] = sc.nTok; r[7] = sc.nDirty[0];
+      r[4] = sc.serialSC; r[5] = sc.innerSerial; r[6] = sc.nDirty[1] | (sc.nDirty[2] << 16); r[7] = sc.nDirty[0];
     }
     __syncthreads();
     if (fOk) { const uint32_t src = fin.last; for (uint32_t k = threadIdx.x; k < fLen; k += blockDim.x) B.out[fPos + k] = B.in[src + k]; }
@@ -470,7 +470,8 @@ template <int W, int BA, int V, class SymT> struct EncCta
     if (nDirty == 0) { finish(B, fin, total.bytes, total.ntok); return; }
     if (round < E2_ROUNDS - 1) return;
 
-    // sequential repair from the first inconsistent super-chunk (its scanned incoming state is exact)
+    // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
+    // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA, parallel inside)
     if (t == 0) { S.bcSt = B.scIn[firstDirty]; if (K) S.bcLut = B.scLut[firstDirty]; }
     __syncthreads();
     AutoState run = S.bcSt; Lut runLut; if (K) runLut = S.bcLut; else lut_init(runLut, W);
@@ -480,8 +481,15 @@ template <int W, int BA, int V, class SymT> struct EncCta
     for (uint32_t s = firstDirty; s < nSC; s++)
     {
       Seg tot;
-      process(B, S, s, true, run, runLut, tot);
-      if (t == 0) { B.scIn[s] = run; if (K) B.scLut[s] = runLut; B.scBase[s] = runBytes; B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
+      bool need = B.scDirty[s] != 0 || B.scIn[s] != run;               // uniform: every thread reads the same words
+      if (K && !need) need = !lut_equal(B.scLut[s], runLut, K);
+      if (need)
+      {
+        process(B, S, s, true, run, runLut, tot);
+        if (t == 0) { B.scIn[s] = run; if (K) B.scLut[s] = runLut; B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
+      }
+      else { tot.cs = B.scSum[s]; if (K) tot.agg = B.scAgg[s]; else tot.agg.m = 0; tot.bytes = B.scBytes[s]; tot.ntok = B.scTok[s]; }
+      if (t == 0) B.scBase[s] = runBytes;
       segsum_apply<K>(run, runLut, tot);
       runBytes += tot.bytes; runTok += tot.ntok;
     }

@@ -25,6 +25,8 @@ hs.compress_device_async(name, t_in[0], t_out, ws, res[:8], sp)
 torch.cuda.synchronize()
 r = int(res[0].item())
 assert r > 0, res
+hs.decompress_device_async(name, t_out, r, t_dec, n, ws, res[8:], sp)   # warm-up (lazy module load)
+torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 ev[0].record()
 if what in ("enc", "both"):
