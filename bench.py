@@ -203,21 +203,39 @@ def run_gpu_arm(args):
 
     # inputs rotated over 4 distinct copies (352 MB > 126 MB L2) so no call finds its input in L2
     NCOPY = 4
+    NSTREAM = args.streams
     t_in = [torch.from_numpy(data).to(dev) for _ in range(NCOPY)]
-    t_dec = [torch.empty(n + 128, dtype=torch.uint8, device=dev) for _ in range(2)]
     t_comp = {c: torch.empty(cap, dtype=torch.uint8, device=dev) for c in CODEC_SET}
     ws_size = max(max(hs.compress_workspace_size(c, n) for c in CODEC_SET), max(hs.decompress_workspace_size(c, cap, n) for c in CODEC_SET))
-    t_ws = torch.empty(ws_size, dtype=torch.uint8, device=dev)
+    # the codec calls of a step are independent: they are dealt round-robin to NSTREAM CUDA streams (own workspace and
+    # decode buffer each), so one call's latency-bound resolve/scan kernels overlap another call's bandwidth kernels
+    side = [torch.cuda.Stream(device=dev) for _ in range(NSTREAM)]
+    t_ws = [torch.empty(ws_size, dtype=torch.uint8, device=dev) for _ in range(NSTREAM)]
+    t_dec = [torch.empty(n + 128, dtype=torch.uint8, device=dev) for _ in range(NSTREAM)]
     t_res = {c: torch.zeros(16, dtype=torch.int32, device=dev) for c in CODEC_SET}
     csize = {}
 
-    def enqueue_step(k):
+    def enqueue_step(k, on=None):
         for i, c in enumerate(CODEC_SET):
-            hs.compress_device_async(c, t_in[(k + i) % NCOPY], t_comp[c], t_ws, t_res[c][:8], sp)
-            hs.decompress_device_async(c, t_comp[c], csize.get(c, cap), t_dec[i % 2], n, t_ws, t_res[c][8:], sp)
+            j = i % NSTREAM
+            q = (on if on is not None else side[j]).cuda_stream
+            hs.compress_device_async(c, t_in[(k + i) % NCOPY], t_comp[c], t_ws[j], t_res[c][:8], q)
+            hs.decompress_device_async(c, t_comp[c], csize.get(c, cap), t_dec[j], n, t_ws[j], t_res[c][8:], q)
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for s_ in side:
+            s_.wait_event(ev)
+
+    def join():
+        for s_ in side:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            stream.wait_event(ev)
 
     # first pass: learn the (deterministic) compressed sizes, check correctness
-    enqueue_step(0)
+    fork(); enqueue_step(0); join()
     torch.cuda.synchronize()
     for c in CODEC_SET:
         r = t_res[c].cpu().numpy()
@@ -226,10 +244,13 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    fork()
     for w in range(max(args.warmup, 3)):
         enqueue_step(w)
+    join()
     torch.cuda.synchronize()
-    assert torch.equal(t_dec[(len(CODEC_SET) - 1) % 2][:n], t_in[0]), "decode(encode(x)) != x"
+    for j in range(NSTREAM):
+        assert torch.equal(t_dec[j][:n], t_in[0]), "decode(encode(x)) != x"
 
     def barrier():
         if world > 1:
@@ -241,8 +262,10 @@ def run_gpu_arm(args):
     barrier()
     sampler.mark_begin()
     e0.record(stream)
+    fork()
     for k in range(args.steps):
         enqueue_step(k)
+    join()
     e1.record(stream)
     barrier()
     sampler.mark_end()
@@ -256,25 +279,50 @@ def run_gpu_arm(args):
     bytes_per_step = 2.0 * n * len(CODEC_SET)
     value = world * bytes_per_step * args.steps / (ms * 1e-3) / 1e9
 
-    # ---- e2e: the reference-named host entry points with pinned host buffers (H2D + kernels + D2H timed)
-    h_in = torch.from_numpy(data).pin_memory()
-    h_comp = torch.empty(cap, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(n + 128, dtype=torch.uint8).pin_memory()
+    # ---- e2e: the reference-named host entry points with pinned host buffers (H2D + kernels + D2H timed).
+    # The entry points are re-entrant like the reference's; NTHREAD host threads each call them on their own pinned
+    # buffers (one codec per call), so one call's H2D overlaps another's kernels and D2H (PCIe is full duplex).
+    NTHREAD = args.threads
+    h_in = [torch.from_numpy(data).pin_memory() for _ in range(NTHREAD)]
+    h_comp = [torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(NTHREAD)]
+    h_out = [torch.empty(n + 128, dtype=torch.uint8).pin_memory() for _ in range(NTHREAD)]
     u8p = ctypes.POINTER(ctypes.c_uint8)
     from common import CODEC_BY_NAME
+    fns = {}
+    for c in CODEC_SET:
+        cd = CODEC_BY_NAME[c]
+        f = getattr(hs.lib, cd.cname); f.restype = ctypes.c_uint32; f.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32]
+        g = getattr(hs.lib, cd.dname); g.restype = ctypes.c_uint32; g.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32]
+        fns[c] = (f, g)
 
     def e2e_step():
-        h2d = d2h = 0
-        for c in CODEC_SET:
-            cd = CODEC_BY_NAME[c]
-            f = getattr(hs.lib, cd.cname); f.restype = ctypes.c_uint32; f.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32]
-            g = getattr(hs.lib, cd.dname); g.restype = ctypes.c_uint32; g.argtypes = [u8p, ctypes.c_uint32, u8p, ctypes.c_uint32]
-            r = f(ctypes.cast(h_in.data_ptr(), u8p), n, ctypes.cast(h_comp.data_ptr(), u8p), cap)
-            d = g(ctypes.cast(h_comp.data_ptr(), u8p), r, ctypes.cast(h_out.data_ptr(), u8p), n + 128)
-            assert r == csize[c] and d == n, (c, r, d, hs.last_error())
-            h2d += n + r
-            d2h += r + n
-        return h2d, d2h
+        todo = list(CODEC_SET)
+        lock = threading.Lock()
+        moved = [0, 0]
+        errs = []
+
+        def work(j):
+            torch.cuda.set_device(local)
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    c = todo.pop()
+                f, g = fns[c]
+                r = f(ctypes.cast(h_in[j].data_ptr(), u8p), n, ctypes.cast(h_comp[j].data_ptr(), u8p), cap)
+                d = g(ctypes.cast(h_comp[j].data_ptr(), u8p), r, ctypes.cast(h_out[j].data_ptr(), u8p), n + 128)
+                if r != csize[c] or d != n:
+                    errs.append((c, r, d, hs.last_error()))
+                with lock:
+                    moved[0] += n + r
+                    moved[1] += r + n
+        ts = [threading.Thread(target=work, args=(j,)) for j in range(NTHREAD)]
+        for t_ in ts:
+            t_.start()
+        for t_ in ts:
+            t_.join()
+        assert not errs, errs
+        return moved[0], moved[1]
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
@@ -289,7 +337,8 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e_value = world * bytes_per_step * e2e_steps / dt / 1e9
-    assert np.array_equal(h_out[:n].numpy(), data)
+    for j in range(NTHREAD):
+        assert np.array_equal(h_out[j][:n].numpy(), data)
 
     if rank != 0:
         if world > 1:
@@ -299,7 +348,7 @@ def run_gpu_arm(args):
     # ---- per-kernel CUDA-event timing on the launching stream (one extra pass, not the timed region)
     buf = ctypes.create_string_buffer(8192)
     hs.lib.hsrle_timing_begin()
-    enqueue_step(0)
+    enqueue_step(0, on=stream)
     hs.lib.hsrle_timing_end(buf, 8192)
     kt = parse_timing(buf.value.decode())
     tot_ms = sum(v[1] for v in kt.values())
@@ -325,16 +374,16 @@ def run_gpu_arm(args):
 
     # ---- per-codec detail (device-resident, CUDA events, 3 reps each)
     detail = {}
-    for i, c in enumerate(CODEC_SET):
+    for i, c in enumerate([] if args.quick else CODEC_SET):
         a, b, d = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         reps = 3
         torch.cuda.synchronize()
         a.record(stream)
         for k in range(reps):
-            hs.compress_device_async(c, t_in[k % NCOPY], t_comp[c], t_ws, t_res[c][:8], sp)
+            hs.compress_device_async(c, t_in[k % NCOPY], t_comp[c], t_ws[0], t_res[c][:8], sp)
         b.record(stream)
         for k in range(reps):
-            hs.decompress_device_async(c, t_comp[c], csize[c], t_dec[k % 2], n, t_ws, t_res[c][8:], sp)
+            hs.decompress_device_async(c, t_comp[c], csize[c], t_dec[k % NSTREAM], n, t_ws[0], t_res[c][8:], sp)
         d.record(stream)
         torch.cuda.synchronize()
         te, td = a.elapsed_time(b) / reps, b.elapsed_time(d) / reps
@@ -343,21 +392,24 @@ def run_gpu_arm(args):
 
     # ---- CPU baseline: the reference's single-threaded CPU path on a bounded sample (rank 0, N=1 only)
     cpu = None
-    if world == 1:
+    if world == 1 and not args.quick:
         kind, enc, dec = cpu_reference_lib()
-        sample_n = N_BYTES // 4
-        sdata = data[:sample_n].copy()
-        dt = cpu_step(enc, dec, sdata, CODEC_SET, 1)
-        cpu = {"value": round(2.0 * sample_n * len(CODEC_SET) / dt / 1e9, 4), "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": f"first {sample_n} B of the stream, all {len(CODEC_SET)} codecs encode+decode once, 1 thread ({dt:.1f} s)"}
+        cpu_step(enc, dec, data, CODEC_SET[:2], 1)     # warm the host caches / page in the library
+        reps, dt = 0, 0.0
+        while dt < 10.0 and reps < 64:                 # bounded sample: about 10 s of single-thread CPU work
+            dt += cpu_step(enc, dec, data, CODEC_SET, 1)
+            reps += 1
+        cpu = {"value": round(2.0 * n * len(CODEC_SET) * reps / dt / 1e9, 4), "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"the full {n}-B stream, all {len(CODEC_SET)} codecs encode+decode, {reps} passes, 1 thread ({dt:.1f} s)"}
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "codecs": CODEC_SET, "bytes_per_codec": n, "per_gpu": "every rank runs the full workload on its own copy",
+            "config": {"workload": WORKLOAD, "codecs": CODEC_SET, "bytes_per_codec": n, "per_gpu": "every rank runs the full workload on its own copy", "streams": NSTREAM,
                        "l2": "inputs rotated over 4 distinct 88 MB copies (352 MB > 126 MB L2); 17 distinct compressed buffers"},
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "reference-named host entry points (rleNN_*_compress/_decompress), pinned host buffers", "steps": e2e_steps},
+                    "api": "reference-named host entry points (rleNN_*_compress/_decompress), pinned host buffers", "steps": e2e_steps,
+                    "host_threads": NTHREAD},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "per_codec": detail}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -370,6 +422,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip the CPU baseline and the per-codec detail (sweeps)")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent codec calls of a step are dealt to")
+    ap.add_argument("--threads", type=int, default=4, help="host threads calling the host-pointer entry points in the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -16,6 +16,7 @@
 #include "hsrle_dispatch.h"
 #include "hsrle_enc_kernels.cuh"
 #include "hsrle_dec_kernels.cuh"
+#include "hsrle_slice_kernels.cuh"
 
 namespace hsrle {
 
@@ -24,7 +25,8 @@ static std::atomic<uint64_t> g_launches{0};
 
 // optional per-kernel CUDA-event timing (bench.py's roofline leg); off by default
 struct TimedLaunch { const char *name; cudaEvent_t a, b; };
-static bool g_timing = false;
+static std::atomic<bool> g_timing{false};
+static std::mutex g_timedMu;
 static std::vector<TimedLaunch> g_timed;
 
 #define HSRLE_LAUNCH_NAMED(name, kern, grid, block, smem, stream, ...)     \
@@ -32,7 +34,7 @@ static std::vector<TimedLaunch> g_timed;
     TimedLaunch tl_{ name, nullptr, nullptr };                             \
     if (g_timing) { cudaEventCreate(&tl_.a); cudaEventCreate(&tl_.b); cudaEventRecord(tl_.a, (stream)); } \
     kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
-    if (g_timing) { cudaEventRecord(tl_.b, (stream)); g_timed.push_back(tl_); } \
+    if (tl_.a) { cudaEventRecord(tl_.b, (stream)); std::lock_guard<std::mutex> lk_(g_timedMu); g_timed.push_back(tl_); } \
     g_launches.fetch_add(1, std::memory_order_relaxed);                    \
   } while (0)
 #define HSRLE_LAUNCH(kern, grid, block, smem, stream, ...) HSRLE_LAUNCH_NAMED(#kern, kern, grid, block, smem, stream, __VA_ARGS__)
@@ -178,7 +180,7 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   size_t zeroBytes = 0;
   const size_t need = enc_carve(B, sp, n, ws, &zeroBytes);
   if (need > wsSize) { g_err = "workspace too small"; return 1; }
-  B.in = dIn; B.out = dOut; B.cap = cap; B.dResult = dResult;
+  B.in = dIn; B.out = dOut; B.cap = cap; B.dResult = dResult; B.outBase = (uint32_t)sp.hdr;
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
@@ -187,6 +189,77 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one stream encoded by several GPUs: per-rank phases between the all-gathers (hsrle_slice.cuh)
+static size_t slice_carve(EncBufs &B, const Spec &sp, uint32_t n, uint32_t lo, uint32_t hi, int rank, int world, void *ws, size_t *zeroBytes)
+{
+  const uint32_t len = hi - lo;
+  const size_t base = enc_carve(B, sp, len ? len : 1, ws, zeroBytes);     // record / chunk capacities from the slice length
+  Carver cv{ (uint8_t *)ws, base };
+  B.sliceIn = cv.take<SliceState>(1);
+  B.n = n;
+  B.sliceMode = 1; B.rank = (uint32_t)rank; B.world = (uint32_t)world; B.sliceLo = lo; B.sliceHi = hi;
+  B.vecBase = lo / 16;
+  const bool last = rank == world - 1;
+  const uint32_t nVecGlobal = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
+  const uint32_t vecs = last ? nVecGlobal - B.vecBase : len / 16;
+  B.nVec = vecs;
+  B.nTiles = (vecs + E1_TILE_VECS - 1) / E1_TILE_VECS;
+  B.lastVec = last ? (n - 1) >> 4 : hi / 16;        // non-last ranks may load the first vector of the tail halo
+  B.maxRuns += 2;
+  B.outBase = SLICE_PORCH;
+  return cv.off + 256;
+}
+
+static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
+{
+  Spec sp;
+  if (!J || !spec_from_codec(J->codec, sp) || !J->dIn || !J->dOut || !J->dWorkspace || !J->dMsg || !J->dAll || !J->dResult) { g_err = "bad argument"; return 1; }
+  if (J->world < 1 || J->world > 64 || J->rank < 0 || J->rank >= J->world || J->n == 0 || J->lo > J->hi || J->hi > J->n) { g_err = "bad slice"; return 1; }
+  if ((J->lo % SLICE_ALIGN) || (J->rank != J->world - 1 && (J->hi % SLICE_ALIGN)) || (J->rank == J->world - 1 && J->hi != J->n) || (J->rank == 0 && J->lo != 0))
+  { g_err = "slice bounds must be multiples of 128 KiB and cover [0, n)"; return 1; }
+  if ((uint64_t)J->n + 64 >= 0xFFFFFFF0ull) { g_err = "stream too long for one frame"; return 1; }
+  if (((uintptr_t)J->dIn & 15) || ((uintptr_t)J->dOut & 15) || ((uintptr_t)J->dWorkspace & 255)) { g_err = "device pointers must be 16-byte aligned (workspace 256)"; return 1; }
+  const EncKernels *k = enc_kernels_for(J->codec);
+  if (!k) { g_err = "codec not built"; return 1; }
+  if (!enc_prepare(J->codec, k)) return 2;
+  EncBufs B; memset(&B, 0, sizeof(B));
+  size_t zeroBytes = 0;
+  const size_t need = slice_carve(B, sp, J->n, J->lo, J->hi, J->rank, J->world, J->dWorkspace, &zeroBytes);
+  if (need > J->workspaceSize) { g_err = "workspace too small"; return 1; }
+  // absolute addressing: byte p of the input is B.in[p]; the rank's buffer starts SLICE_FRONT bytes before its slice
+  B.in = J->dIn + SLICE_FRONT - (ptrdiff_t)J->lo;
+  B.out = J->dOut; B.cap = J->outCap; B.dResult = J->dResult;
+  B.msg = reinterpret_cast<SliceMsg *>(J->dMsg); B.all = reinterpret_cast<const SliceMsg *>(J->dAll);
+  const int sms = num_sms();
+  const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
+  switch (phase)
+  {
+    case 0:   // scan
+      if (!cuda_ok(cudaMemsetAsync(J->dWorkspace, 0, zeroBytes, st), "memset")) return 2;
+      if (B.nTiles) HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
+      HSRLE_LAUNCH(k_enc_slice_msg1, 1, 32, 0, st, B);
+      break;
+    case 1:   // boundary-run fix-up, automaton from the assumed incoming state
+      HSRLE_LAUNCH(k_enc_slice_link, 1, 32, 0, st, B, sp);
+      for (int r = 0; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      break;
+    case 2:   // true incoming state, repair rounds
+      HSRLE_LAUNCH(k_enc_slice_inject, 1, 32, 0, st, B, sp);
+      for (int r = 1; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      break;
+    case 3:   // tokens
+      HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
+      HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
+      break;
+    case 4:   // closing header, trailing literal, stream header, result
+      HSRLE_LAUNCH(k_enc_slice_finish, sms * 2, 256, 0, st, B, sp);
+      break;
+    default: g_err = "bad phase"; return 1;
+  }
+  return cuda_ok(cudaGetLastError(), "slice launch") ? 0 : 2;
 }
 
 static std::mutex g_dattrMu;
@@ -233,6 +306,9 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
 
 // ------------------------------------------------------------------------------------------------
 // library-owned context for the synchronous entry points
+// One context per call in flight: the reference's entry points are re-entrant pure functions
+// (src/simd_platform.c:100-103 is their only shared state), so concurrent callers must not serialise here either;
+// each call owns a stream, staging buffers and a workspace and overlaps with the other threads' transfers and kernels.
 struct Context
 {
   std::mutex mu;
@@ -269,16 +345,40 @@ struct Context
     return true;
   }
 };
-static Context g_ctx;
+// Contexts live in a pool: a call takes a free one (or creates one) and gives it back when it returns, so threads
+// that come and go keep re-using the same streams and device buffers.
+static std::mutex g_poolMu;
+static std::vector<Context *> g_pool;
+struct ContextLease
+{
+  Context *c;
+  ContextLease()
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+    std::lock_guard<std::mutex> lk(g_poolMu);
+    c = nullptr;
+    for (size_t i = g_pool.size(); i-- > 0;)     // streams and buffers belong to the device they were created on
+      if (g_pool[i]->dev == cur || !g_pool[i]->tried) { c = g_pool[i]; g_pool.erase(g_pool.begin() + i); break; }
+    if (!c) c = new Context();
+  }
+  ~ContextLease() { std::lock_guard<std::mutex> lk(g_poolMu); g_pool.push_back(c); }
+};
 static void set_func_attrs() {}
 
-static uint32_t run_sync(bool compress, int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
+static uint32_t run_sync(Context &C, bool compress, int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
 {
-  Context &C = g_ctx;
   Spec sp;
   if (!spec_from_codec(codec, sp)) return 0;
-  EncBufs B; DecBufs D;
-  const size_t need = compress ? enc_carve(B, sp, inSize, nullptr, nullptr) : dec_carve(D, sp, inSize, outSize, nullptr, nullptr);
+  // size the context's workspace for the hungriest codec at this input size, so that a pooled context never has to
+  // re-allocate (cudaFree synchronises the device) when it meets another codec
+  size_t need = 0;
+  for (int id = 0; id < 48; id++)
+  {
+    Spec s2; if (!spec_from_codec(id, s2)) continue;
+    EncBufs B; DecBufs D;
+    need = std::max(need, compress ? enc_carve(B, s2, inSize, nullptr, nullptr) : dec_carve(D, s2, inSize, outSize, nullptr, nullptr));
+  }
   if (!C.grow(&C.ws, &C.wsSize, need)) return 0;
   const int rc = compress ? enc_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream)
                           : dec_enqueue(codec, dIn, inSize, dOut, outSize, C.ws, C.wsSize, C.dResult, C.stream);
@@ -367,28 +467,27 @@ int hsrle_decompress_device_async(int codec, const uint8_t *dIn, uint32_t inSize
 
 uint32_t hsrle_compress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
 {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (!g_ctx.init()) return 0;
-  return run_sync(true, codec, dIn, inSize, dOut, outSize);
+  ContextLease L; Context &C = *L.c;
+  if (!C.init()) return 0;
+  return run_sync(C, true, codec, dIn, inSize, dOut, outSize);
 }
 uint32_t hsrle_decompress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
 {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (!g_ctx.init()) return 0;
-  return run_sync(false, codec, dIn, inSize, dOut, outSize);
+  ContextLease L; Context &C = *L.c;
+  if (!C.init()) return 0;
+  return run_sync(C, false, codec, dIn, inSize, dOut, outSize);
 }
 
 uint32_t hsrle_compress_host(int codec, const uint8_t *pIn, uint32_t inSize, uint8_t *pOut, uint32_t outSize)
 {
   // preconditions of the reference: src/rle8_extreme_cpu.h:88, src/rleX_extreme_cpu.h:49, src/rleX_Xsl.h:271
   if (pIn == NULL || inSize == 0 || pOut == NULL || outSize < rle_compress_bounds(inSize)) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  Context &C = g_ctx;
+  ContextLease L; Context &C = *L.c;
   if (!C.init()) return 0;
   if (!C.grow((void **)&C.dIn, &C.dInSize, (size_t)inSize + 64)) return 0;
   if (!C.grow((void **)&C.dOut, &C.dOutSize, (size_t)outSize + 64)) return 0;
   if (!cuda_ok(cudaMemcpyAsync(C.dIn, pIn, inSize, cudaMemcpyHostToDevice, C.stream), "H2D")) return 0;
-  const uint32_t r = run_sync(true, codec, C.dIn, inSize, C.dOut, outSize);
+  const uint32_t r = run_sync(C, true, codec, C.dIn, inSize, C.dOut, outSize);
   if (r == 0) return 0;
   if (!cuda_ok(cudaMemcpyAsync(pOut, C.dOut, r, cudaMemcpyDeviceToHost, C.stream), "D2H")) return 0;
   if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
@@ -403,17 +502,26 @@ uint32_t hsrle_decompress_host(int codec, const uint8_t *pIn, uint32_t inSize, u
   uint32_t n, clen; memcpy(&n, pIn, 4); memcpy(&clen, pIn + 4, 4);
   if (n > outSize || clen > inSize || clen < 8) return 0;
   if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  Context &C = g_ctx;
+  ContextLease L; Context &C = *L.c;
   if (!C.init()) return 0;
   if (!C.grow((void **)&C.dIn, &C.dInSize, (size_t)clen + 64)) return 0;
   if (!C.grow((void **)&C.dOut, &C.dOutSize, (size_t)n + 64)) return 0;
   if (!cuda_ok(cudaMemcpyAsync(C.dIn, pIn, clen, cudaMemcpyHostToDevice, C.stream), "H2D")) return 0;
-  const uint32_t r = run_sync(false, codec, C.dIn, clen, C.dOut, n);
+  const uint32_t r = run_sync(C, false, codec, C.dIn, clen, C.dOut, n);
   if (r == 0) return 0;
   if (!cuda_ok(cudaMemcpyAsync(pOut, C.dOut, r, cudaMemcpyDeviceToHost, C.stream), "D2H")) return 0;
   if (!cuda_ok(cudaStreamSynchronize(C.stream), "synchronize")) return 0;
   return r;
+}
+
+size_t hsrle_slice_workspace_size(int codec, uint32_t sliceBytes)
+{
+  Spec sp; if (!spec_from_codec(codec, sp)) return 0;
+  EncBufs B; return slice_carve(B, sp, sliceBytes ? sliceBytes : 1, 0, sliceBytes, 0, 1, nullptr, nullptr);
+}
+int hsrle_slice_compress_phase(const hsrle_slice_job *job, int phase, void *cudaStream)
+{
+  return slice_phase(job, phase, (cudaStream_t)cudaStream);
 }
 
 void hsrle_timing_begin(void)
@@ -444,7 +552,7 @@ int hsrle_timing_end(char *buf, int bufSize)
 }
 
 const char *hsrle_last_error(void) { return g_err.c_str(); }
-int hsrle_device(void) { std::lock_guard<std::mutex> lk(g_ctx.mu); g_ctx.init(); return g_ctx.dev; }
+int hsrle_device(void) { ContextLease L; L.c->init(); return L.c->dev; }
 uint64_t hsrle_kernel_launches(void) { return g_launches.load(); }
 
 #define HSRLE_PAIR(cname, dname, bits, ba, var)                                                                                   \

@@ -54,6 +54,8 @@ struct EncScalars
   uint32_t serialSC;                      // super-chunks repaired sequentially (diagnostics)
   uint32_t innerSerial;                   // super-chunks that needed the in-CTA sequential pass (diagnostics)
   uint64_t tokBytes;                      // sum over tokens of header + literal bytes
+  uint32_t endShift;                      // slices: start record i pairs with end record i + endShift (hsrle_slice.cuh)
+  uint32_t nStarts, nEnds;                // slices: records found by the scan
 };
 
 struct CopyDesc { uint32_t dst, src, len; };
@@ -108,6 +110,14 @@ struct EncBufs
   CopyDesc *bigList, *medList;
   EncScalars *sc;
   uint32_t *dResult;
+  // one stream encoded by several GPUs (hsrle_slice.cuh); all zero / null for a whole-stream call
+  uint32_t sliceMode, rank, world;
+  uint32_t sliceLo, sliceHi;             // this rank's input range; literal bytes below sliceLo belong to earlier ranks
+  uint32_t vecBase;                      // first 16-byte vector of the slice
+  uint32_t outBase;                      // stream offset (whole stream) / local offset (slice) of the first token
+  struct SliceState *sliceIn;            // incoming automaton state of the slice
+  struct SliceMsg *msg;                  // this rank's message
+  const struct SliceMsg *all;            // everybody's messages after the all-gather
 };
 
 // ---------------------------------------------------------------- E1 helpers (host+device)

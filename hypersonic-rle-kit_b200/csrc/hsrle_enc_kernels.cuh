@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hsrle_enc.cuh"
+#include "hsrle_slice.cuh"
 
 namespace hsrle {
 
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
   const uint32_t n = B.n, lastVec = B.lastVec;
   const uint8_t *__restrict__ in = B.in;
   const uint4 *in16 = reinterpret_cast<const uint4 *>(in);
-  const uint32_t vw = tile * E1_TILE_VECS + warp * (32 * E1_STEPS);   // first vector of this warp's span
+  const uint32_t vw = B.vecBase + tile * E1_TILE_VECS + warp * (32 * E1_STEPS);   // first vector of this warp's span
 
   // ---- phase A: masks and per-step totals (no block barrier); loads run one group of 4 steps ahead
   uint32_t c2 = 0, c3 = 0;                 // the 8 input bytes before the current step
@@ -178,7 +179,9 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
     {
       const unsigned long long tot = exclusive + agg;
       const uint32_t nS = (uint32_t)(tot & 0x7FFFFFFFull), nE = (uint32_t)(tot >> 31);
-      if (nS != nE || nS > B.maxRuns) { sc.status = ST_BADARG; sc.nRuns = 0; sc.nSC = 0; }
+      sc.nStarts = nS; sc.nEnds = nE;
+      if (B.sliceMode) { if (nS > B.maxRuns || nE > B.maxRuns) sc.status = ST_BADARG; }    // paired up by k_enc_slice_link
+      else if (nS != nE || nS > B.maxRuns) { sc.status = ST_BADARG; sc.nRuns = 0; sc.nSC = 0; }
       else { sc.nRuns = nS; sc.nSC = (nS + E2_SCR - 1) / E2_SCR; }
     }
   }
@@ -227,6 +230,13 @@ __device__ __forceinline__ void enc_push_copy(const EncBufs &B, uint32_t dst, ui
 // padded record index: one pad slot per chunk keeps the CH-records-per-thread accesses conflict free
 __device__ __forceinline__ int rec_slot(int j) { return j + j / E2_CH; }
 
+// state the automaton starts from: the stream's initial state, or the slice's incoming state (hsrle_slice.cuh)
+__device__ __forceinline__ void enc_stream_incoming(const EncBufs &B, int W, AutoState &st, Lut &lut)
+{
+  if (B.sliceMode) { st = B.sliceIn->st; lut = B.sliceIn->lut; }
+  else { st = enc_initial_state(); lut_init(lut, W); }
+}
+
 template <int W, int BA, int V, class SymT> struct EncCta
 {
   static constexpr int K = (V == V_LUT3) ? 3 : (V == V_LUT7 ? 7 : 0);
@@ -246,7 +256,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
 
   // evaluate records [j0,j1) (local indices) from (st,lut); returns the segment summary
   template <bool COUNT_ONLY>
-  static __device__ __forceinline__ Seg eval_range(const Smem &S, uint32_t n, int j0, int j1, AutoState &st, Lut &lut)
+  static __device__ __forceinline__ Seg eval_range(const Smem &S, uint32_t n, uint32_t floor, int j0, int j1, AutoState &st, Lut &lut)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     Seg r = segsum_identity<K>();
@@ -258,7 +268,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       const uint32_t lastBefore = st.last;
       const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &r.agg : nullptr, s, e, h);
       fl |= ev;
-      if (ev & EV_EMIT) { r.bytes += h.len + (s - lastBefore); r.ntok++; }
+      if (ev & EV_EMIT) { r.bytes += h.len + slice_lit_len(lastBefore, s, floor); r.ntok++; }
     }
     r.cs.flags = fl; r.cs.last = st.last; r.cs.cursor = st.cursor; r.cs.lastSym = st.lastSym;
     return r;
@@ -305,7 +315,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
   static __device__ void process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
   {
     constexpr Spec sp = make_spec(W, BA, V);
-    const uint32_t nRuns = B.sc->nRuns, n = B.n;
+    const uint32_t nRuns = B.sc->nRuns, n = B.n, floor = B.sliceLo, endShift = B.sc->endShift;
     const uint32_t lo = s * E2_SCR;
     const uint32_t cnt = min((uint32_t)E2_SCR, nRuns - lo);
     const int halo = (s > 0) ? E2_WARM : 0;
@@ -315,7 +325,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     {
       const uint32_t g = lo + j - E2_WARM;
       const int q = rec_slot(j);
-      S.a[q] = B.runA[g]; S.b[q] = B.runB[g]; S.sym[q] = runSym[g];
+      S.a[q] = B.runA[g]; S.b[q] = B.runB[g + endShift]; S.sym[q] = runSym[g];
     }
     __syncthreads();
     const int t = threadIdx.x;
@@ -325,15 +335,15 @@ template <int W, int BA, int V, class SymT> struct EncCta
 
     AutoState stIn; Lut lutIn;
     if (t == 0 && given) { stIn = gSt; lutIn = gLut; }
-    else if (t == 0 && s == 0) { stIn = enc_initial_state(); lut_init(lutIn, W); }
+    else if (t == 0 && s == 0) enc_stream_incoming(B, W, stIn, lutIn);
     else
     { // warm up over the preceding E2_WARM records from the neutral guess
       const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
       enc_neutral_state(sp, (active && w0 < j0) ? S.a[rec_slot(w0)] : 0u, stIn, lutIn);
-      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<true>(S, n, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<true>(S, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
     }
     Seg mine = segsum_identity<K>();
-    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, j0, j1, st, lut); }
+    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut); }
 
     // fixed point of (scan -> compare -> re-run)
     AutoState st0; Lut lut0;   // incoming state of the super-chunk = what thread 0 used
@@ -351,7 +361,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       if (active && t > 0 && state_differs(want, wantLut, stIn, lutIn))
       {
         stIn = want; lutIn = wantLut; changed = 1;
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, j0, j1, st, lut);
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut);
       }
       if (!__syncthreads_or(changed)) { converged = true; break; }
     }
@@ -364,7 +374,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         {
           S.serSt[c] = st; if (K) S.serLut[K ? c : 0] = lut;
           const int a0 = E2_WARM + c * E2_CH, a1 = min(a0 + E2_CH, E2_WARM + (int)cnt);
-          (void)eval_range<true>(S, n, a0, a1, st, lut);
+          (void)eval_range<true>(S, n, floor, a0, a1, st, lut);
         }
         atomicAdd(&B.sc->innerSerial, 1u);
       }
@@ -372,7 +382,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       if (active)
       {
         stIn = S.serSt[t]; if (K) lutIn = S.serLut[K ? t : 0];
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, j0, j1, st, lut);
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut);
       }
       (void)block_excl_scan(S, mine, total);
     }
@@ -393,18 +403,32 @@ template <int W, int BA, int V, class SymT> struct EncCta
   }
 
   // ---- run by the last CTA of a round: scan of the super-chunk summaries, verification, finishing
-  static __device__ void finish(const EncBufs &B, const AutoState &fin, uint64_t tokBytes, uint32_t nTok)
+  static __device__ void finish(const EncBufs &B, const AutoState &fin, const Lut &finLut, uint64_t tokBytes, uint32_t nTok)
   { // all threads call; thread 0 writes header/terminator, everybody copies a short trailing literal
     constexpr Spec sp = make_spec(W, BA, V);
     EncScalars &sc = *B.sc;
     __shared__ uint32_t fPos, fLen, fOk;
+    if (B.sliceMode)
+    { // a slice only reports: outgoing state and token bytes (placement happens after the size exchange)
+      if (threadIdx.x == 0)
+      {
+        sc.tokBytes = tokBytes; sc.nTok = nTok;
+        if (sc.status == ST_OK && (uint64_t)B.outBase + tokBytes + 64 > B.cap) sc.status = ST_OVERFLOW;
+        SliceMsg &m = *B.msg;
+        m.out = fin; if (K) m.outLut = finLut; else lut_init(m.outLut, W);
+        m.tokBytes = tokBytes; m.status = sc.status;
+        uint32_t *r = B.dResult;
+        r[0] = 0; r[1] = sc.status; r[2] = sc.nRuns; r[3] = sc.nSC; r[4] = sc.serialSC; r[5] = sc.innerSerial; r[6] = 0; r[7] = sc.nDirty[0];
+      }
+      return;
+    }
     if (threadIdx.x == 0)
     {
       fOk = 0;
       sc.tokBytes = tokBytes; sc.nTok = nTok;
       const uint32_t L = B.n - fin.last;
       TokenHdr h; enc_terminator(sp, L, h);
-      const uint64_t total = (uint64_t)sp.hdr + tokBytes + h.len + L;
+      const uint64_t total = (uint64_t)B.outBase + tokBytes + h.len + L;
       if (sc.status == ST_OK && (total > B.cap || total >= 0xFFFFFFF0ull)) sc.status = ST_OVERFLOW;
       if (sc.status == ST_OK)
       {
@@ -413,7 +437,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         const uint32_t nn = B.n, tt = (uint32_t)total;
         for (int k = 0; k < 4; k++) { o[k] = (uint8_t)(nn >> (8 * k)); o[4 + k] = (uint8_t)(tt >> (8 * k)); }
         if (sp.hdr == 9) o[8] = 0;
-        const uint32_t pos = (uint32_t)(sp.hdr + tokBytes);
+        const uint32_t pos = (uint32_t)(B.outBase + tokBytes);
         for (uint32_t k = 0; k < h.len; k++) o[pos + k] = h.b[k];
         if (L >= MED_COPY) enc_push_copy(B, pos + h.len, fin.last, L);
         else { fPos = pos + h.len; fLen = L; fOk = 1; }
@@ -444,7 +468,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     }
     Seg total;
     const Seg pre = block_excl_scan(S, mine, total);
-    AutoState st = enc_initial_state(); Lut lut; lut_init(lut, W);
+    AutoState st; Lut lut; enc_stream_incoming(B, W, st, lut);
     segsum_apply<K>(st, lut, pre);
     uint64_t bytes = pre.bytes;
     uint32_t nd = 0, first = 0xFFFFFFFFu;
@@ -465,9 +489,9 @@ template <int W, int BA, int V, class SymT> struct EncCta
     const uint32_t nDirty = sDirty, firstDirty = sFirst;
     if (t == 0) { sc.nDirty[round] = nDirty; sc.firstDirty[round] = firstDirty; }
     __syncthreads();
-    AutoState fin = enc_initial_state(); Lut finLut; lut_init(finLut, W);
+    AutoState fin; Lut finLut; enc_stream_incoming(B, W, fin, finLut);
     segsum_apply<K>(fin, finLut, total);
-    if (nDirty == 0) { finish(B, fin, total.bytes, total.ntok); return; }
+    if (nDirty == 0) { finish(B, fin, finLut, total.bytes, total.ntok); return; }
     if (round < E2_ROUNDS - 1) return;
 
     // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
@@ -494,7 +518,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       runBytes += tot.bytes; runTok += tot.ntok;
     }
     __syncthreads();
-    finish(B, run, runBytes, runTok);
+    finish(B, run, runLut, runBytes, runTok);
   }
 };
 
@@ -595,7 +619,7 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
   EncScalars &sc = *B.sc;
   if (sc.status != ST_OK) return;
-  const uint32_t nSC = sc.nSC, nRuns = sc.nRuns, n = B.n;
+  const uint32_t nSC = sc.nSC, nRuns = sc.nRuns, n = B.n, floor = B.sliceLo, endShift = sc.endShift;
   const SymT *__restrict__ runSym = reinterpret_cast<const SymT *>(B.runSym);
   const uint8_t *__restrict__ in = B.in;
   uint8_t *__restrict__ out = B.out;
@@ -609,7 +633,7 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     for (int j = t; j < (int)cnt; j += E2_T)
     {
       const int q = rec_slot(j + E2_CH);
-      S.a[q] = B.runA[lo + j]; S.b[q] = B.runB[lo + j]; S.sym[q] = runSym[lo + j];
+      S.a[q] = B.runA[lo + j]; S.b[q] = B.runB[lo + j + endShift]; S.sym[q] = runSym[lo + j];
     }
     __syncthreads();
     const int j0 = E2_CH + t * E2_CH, j1 = min(j0 + E2_CH, E2_CH + (int)cnt);
@@ -627,7 +651,7 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
         uint32_t rs, re; CountSink h;
         const uint32_t lastBefore = st.last;
         const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &dummy : nullptr, rs, re, h);
-        if (ev & EV_EMIT) mine += h.len + (rs - lastBefore);
+        if (ev & EV_EMIT) mine += h.len + slice_lit_len(lastBefore, rs, floor);
       }
     }
     unsigned long long inc = mine;
@@ -638,7 +662,7 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     unsigned long long pre = 0, segLen = 0;
 #pragma unroll
     for (int w = 0; w < E2_T / 32; w++) { const unsigned long long x = S.warpTot[w]; if (w < warp) pre += x; segLen += x; }
-    const uint64_t seg0 = (uint64_t)sp.hdr + B.scBase[s];
+    const uint64_t seg0 = (uint64_t)B.outBase + B.scBase[s];
     uint64_t pos = seg0 + pre + (inc - mine);
     const bool staged = segLen <= E3_STAGE;            // uniform
     const uint32_t shift = (uint32_t)(seg0 & 15);      // keeps stage image and stream equally aligned
@@ -654,12 +678,18 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
         const uint32_t lastBefore = st.last;
         const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &dummy : nullptr, rs, re, h);
         if (!(ev & EV_EMIT)) continue;
-        const uint32_t lit = rs - lastBefore;
+        const uint32_t lit = slice_lit_len(lastBefore, rs, floor), litSrc = slice_lit_src(lastBefore, floor);
+        if (B.sliceMode && pos == B.outBase)
+        { // the slice's first token: whoever holds the start of its literal places this header (hsrle_slice.cuh)
+          SliceMsg &m = *B.msg;
+          m.hasEmit = 1; m.firstHdrLen = h.len; m.firstS = rs; m.firstLast = lastBefore;
+          for (uint32_t k = 0; k < 24; k++) m.firstHdr[k] = k < h.len ? h.p[k] : 0;
+        }
         if (lit)
         {
-          if (staged) { EmitDesc d; d.dst = shift + (uint32_t)(pos - seg0) + h.len; d.src = lastBefore; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
-          else if (lit >= MED_COPY) enc_push_copy(B, (uint32_t)(pos + h.len), lastBefore, lit);
-          else { EmitDesc d; d.dst = (uint32_t)(pos + h.len); d.src = lastBefore; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
+          if (staged) { EmitDesc d; d.dst = shift + (uint32_t)(pos - seg0) + h.len; d.src = litSrc; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
+          else if (lit >= MED_COPY) enc_push_copy(B, (uint32_t)(pos + h.len), litSrc, lit);
+          else { EmitDesc d; d.dst = (uint32_t)(pos + h.len); d.src = litSrc; d.len = lit; S.desc[atomicAdd(&S.nDesc, 1u)] = d; }
         }
         pos += h.len + lit;
       }

@@ -193,6 +193,35 @@ uint32_t hsrle_decompress_device(int codec, const uint8_t *dIn, uint32_t inSize,
 uint32_t hsrle_compress_host(int codec, const uint8_t *pIn, uint32_t inSize, uint8_t *pOut, uint32_t outSize);
 uint32_t hsrle_decompress_host(int codec, const uint8_t *pIn, uint32_t inSize, uint8_t *pOut, uint32_t outSize);
 
+/* ---- One stream encoded by several GPUs (one process per GPU; configs[3] of the benchmark) ------------------
+ * The input of ONE reference-identical stream of n bytes is cut into contiguous slices [lo, hi), one per rank:
+ * lo a multiple of 128 KiB, rank 0 starts at 0, the last rank ends at n.  A rank's input buffer dIn holds the
+ * bytes [lo - 32, hi + 32) of the input (byte 32 of the buffer is input byte lo; halo bytes outside [0, n) may be
+ * anything).  The encode runs in phases with an all-gather of every rank's 256-byte message (dMsg -> dAll, rank
+ * order) after phases 0, 1, 2 and 3 -- NCCL in hsrle_b200.sliced, any transport works:
+ *   phase 0  candidate scan                                   -> all-gather
+ *   phase 1  boundary-run fix-up + emit automaton             -> all-gather
+ *   phase 2  incoming-state check + repair rounds             -> all-gather; repeat phase 2 while any rank's
+ *            message has word 6 ("changed") set (at most `world` times)
+ *   phase 3  tokens                                           -> all-gather
+ *   phase 4  closing header + trailing literal + stream header; dResult = { partLen, status, partStart,
+ *            partOffset, totalStreamBytes, ... }: this rank's share of the stream is dOut[partStart, partStart +
+ *            partLen) and belongs at byte partOffset of the single stream.
+ * dOut needs (hi - lo) + (hi - lo) / 256 + 1024 bytes.  All calls are stream-ordered and never synchronise. */
+typedef struct hsrle_slice_job
+{
+  int codec, rank, world;
+  uint32_t n, lo, hi;
+  const uint8_t *dIn;
+  uint8_t *dOut; uint32_t outCap;
+  void *dWorkspace; size_t workspaceSize;
+  uint32_t *dMsg;            /* 64 words */
+  const uint32_t *dAll;      /* world x 64 words */
+  uint32_t *dResult;         /* 8 words */
+} hsrle_slice_job;
+size_t hsrle_slice_workspace_size(int codec, uint32_t sliceBytes);
+int hsrle_slice_compress_phase(const hsrle_slice_job *job, int phase, void *cudaStream);
+
 /* Last CUDA error text seen by the library on this thread ("" if none) and the device in use (-1 = none). */
 const char *hsrle_last_error(void);
 int hsrle_device(void);

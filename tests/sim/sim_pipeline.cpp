@@ -300,3 +300,154 @@ extern "C" uint32_t sim_decompress(int W, int align, int variant, const uint8_t 
   }
   return sc.n;
 }
+
+// ================================================================================================
+// One stream encoded by several ranks (hsrle_slice.cuh): host-side twin of hsrle_slice_compress_phase, same job
+// struct, host pointers.  The scan and the placement run the product's own HD functions (m16_*, slice_link,
+// slice_lit_*, slice_plan, enc_eval); the automaton is threaded sequentially from the slice's incoming state (its
+// speculative CTA form is covered by sim_compress above and by the GPU parity tests).
+#include "../../hypersonic-rle-kit_b200/csrc/hsrle_slice.cuh"
+#include "../../include/hsrle_b200.h"
+#include <map>
+
+struct SimSlice
+{
+  std::vector<uint32_t> runA, runB; std::vector<uint64_t> runSym;
+  uint32_t endShift = 0, nRuns = 0, status = 0;
+  SliceState in;
+  uint64_t tokBytes = 0;
+};
+static std::map<const void *, SimSlice> g_slices;
+
+template <int W, int MINM> static void sim_scan_slice(const uint8_t *in /* absolute */, uint32_t n, uint32_t lo, uint32_t hi, bool last, SimSlice &S)
+{
+  const uint32_t v0 = lo / 16;
+  const uint32_t v1 = last ? (uint32_t)(((uint64_t)n + 1 + 15) / 16) : hi / 16;
+  auto mask = [&](int64_t v) -> uint32_t
+  { // the halo (32 bytes either side) is real input where it lies inside [0, n)
+    if (v < 0) return 0;
+    uint32_t c[6];
+    for (int j = 0; j < 6; j++)
+    {
+      uint32_t w = 0;
+      for (int k = 0; k < 4; k++) { const int64_t p = v * 16 - 8 + j * 4 + k; if (p >= 0 && p < (int64_t)n && p >= (int64_t)lo - 32 && p < (int64_t)hi + 32) w |= (uint32_t)in[p] << (8 * k); }
+      c[j] = w;
+    }
+    return m16_raw<W>(c) & m16_valid<W>((uint32_t)v, n);
+  };
+  for (uint32_t v = v0; v < v1; v++)
+  {
+    const uint32_t A = (mask((int64_t)v - 1) >> 8) | (mask(v) << 8) | (mask((int64_t)v + 1) << 24);
+    uint32_t s, e;
+    m16_boundaries<MINM>(A, s, e);
+    for (int i = 0; i < 16; i++)
+    {
+      if (s >> i & 1) { const uint32_t a = v * 16 + i; S.runA.push_back(a); S.runSym.push_back(load_sym(in + a - W, W)); }
+      if (e >> i & 1) S.runB.push_back(v * 16 + i);
+    }
+  }
+}
+
+// sequential automaton over the slice's records; emits when out != nullptr
+static void sim_slice_auto(const Spec &sp, const hsrle_slice_job *J, SimSlice &S, const uint8_t *in, SliceMsg &m, uint8_t *out)
+{
+  AutoState st = S.in.st; Lut lut = S.in.lut; LutAgg agg; agg.m = 0;
+  uint64_t pos = SLICE_PORCH, bytes = 0;
+  if (out) m.hasEmit = 0;
+  for (uint32_t j = 0; j < S.nRuns; j++)
+  {
+    uint32_t s, e; TokenHdr h;
+    const uint32_t lastBefore = st.last;
+    const uint32_t ev = enc_eval(sp, S.runSym[j], J->n, S.runA[j], S.runB[j + S.endShift], st, lut, sp.K ? &agg : nullptr, s, e, h);
+    if (!(ev & EV_EMIT)) continue;
+    const uint32_t lit = slice_lit_len(lastBefore, s, J->lo), src = slice_lit_src(lastBefore, J->lo);
+    if (out)
+    {
+      if (pos == SLICE_PORCH)
+      {
+        m.hasEmit = 1; m.firstHdrLen = h.len; m.firstS = s; m.firstLast = lastBefore;
+        for (uint32_t k = 0; k < 24; k++) m.firstHdr[k] = k < h.len ? h.b[k] : 0;
+      }
+      memcpy(out + pos, h.b, h.len); memcpy(out + pos + h.len, in + src, lit);
+    }
+    pos += h.len + lit; bytes += h.len + lit;
+  }
+  S.tokBytes = bytes;
+  m.out = st; if (sp.K) m.outLut = lut; else lut_init(m.outLut, sp.W);
+  m.tokBytes = bytes; m.status = S.status;
+}
+
+extern "C" int sim_slice_compress_phase(const hsrle_slice_job *J, int phase, void *)
+{
+  const int wi = J->codec >> 3, ba = (J->codec >> 2) & 1, var = J->codec & 3;
+  const Spec sp = make_spec(width_from_index(wi), ba, var);
+  const int W = sp.W;
+  SimSlice &S = g_slices[J->dWorkspace];
+  const uint8_t *in = J->dIn + SLICE_FRONT - (ptrdiff_t)J->lo;
+  SliceMsg &m = *reinterpret_cast<SliceMsg *>(J->dMsg);
+  const SliceMsg *all = reinterpret_cast<const SliceMsg *>(J->dAll);
+  const bool last = J->rank == J->world - 1;
+  switch (phase)
+  {
+    case 0:
+      S = SimSlice(); memset(&m, 0, sizeof(m));
+#define SCAN(w, mm) if (W == w && sp.minM == mm) sim_scan_slice<w, mm>(in, J->n, J->lo, J->hi, last, S);
+      SCAN(1, 5) SCAN(1, 2) SCAN(2, 2) SCAN(3, 3) SCAN(4, 4) SCAN(6, 6) SCAN(8, 8)
+#undef SCAN
+      m.lo = J->lo; m.hi = J->hi; m.nStarts = (uint32_t)S.runA.size(); m.nEnds = (uint32_t)S.runB.size();
+      m.firstEnd = S.runB.empty() ? 0u : S.runB[0];
+      return 0;
+    case 1:
+    {
+      const SliceLink L = slice_link(all, J->rank, J->world);
+      if (!L.ok) { S.status = ST_BADARG; S.nRuns = 0; }
+      else
+      {
+        S.endShift = L.endShift; S.nRuns = L.nRuns;
+        if (L.borrow) { S.runB.resize(std::max<size_t>(S.runB.size(), (size_t)L.endShift + L.nRuns)); S.runB[L.endShift + L.nRuns - 1] = L.borrowedEnd; }
+      }
+      slice_guess_state(sp, J->rank, J->lo, S.in);
+      sim_slice_auto(sp, J, S, in, m, nullptr);
+      return 0;
+    }
+    case 2:
+    {
+      SliceState want; slice_incoming_state(sp, all, J->rank, want);
+      const bool changed = slice_state_differs(sp, want, S.in);
+      if (changed) { S.in = want; sim_slice_auto(sp, J, S, in, m, nullptr); }
+      m.changed = changed ? 1u : 0u;
+      return 0;
+    }
+    case 3:
+      sim_slice_auto(sp, J, S, in, m, J->dOut);
+      return 0;
+    case 4:
+    {
+      uint32_t status = S.status;
+      for (int q = 0; q < J->world; q++) if (all[q].status != ST_OK && status == ST_OK) status = all[q].status;
+      SlicePlan P; slice_plan(sp, all, J->rank, J->world, J->n, P);
+      const uint64_t pos = (uint64_t)SLICE_PORCH + all[J->rank].tokBytes;
+      if (status == ST_OK && pos + P.closeLen + P.trailLen > J->outCap) status = ST_OVERFLOW;
+      uint64_t before = 0, total = 0;
+      for (int q = 0; q < J->world; q++) { SlicePlan Q; slice_plan(sp, all, q, J->world, J->n, Q); if (q < J->rank) before += Q.partLen; total += Q.partLen; }
+      if (status == ST_OK)
+      {
+        memcpy(J->dOut + pos, P.closeHdr, P.closeLen);
+        memcpy(J->dOut + pos + P.closeLen, in + P.trailSrc, P.trailLen);
+        if (J->rank == 0)
+        {
+          uint8_t *o = J->dOut + P.partStart;
+          const uint32_t nn = J->n, tt = (uint32_t)total;
+          for (int k = 0; k < 4; k++) { o[k] = (uint8_t)(nn >> (8 * k)); o[4 + k] = (uint8_t)(tt >> (8 * k)); }
+          if (sp.hdr == 9) o[8] = 0;
+        }
+      }
+      uint32_t *r = J->dResult;
+      r[0] = status == ST_OK ? (uint32_t)P.partLen : 0u; r[1] = status; r[2] = P.partStart; r[3] = (uint32_t)before;
+      r[4] = (uint32_t)total; r[5] = S.nRuns; r[6] = 0; r[7] = P.trailLen;
+      g_slices.erase(J->dWorkspace);
+      return 0;
+    }
+  }
+  return 1;
+}
