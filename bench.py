@@ -359,8 +359,7 @@ def run_gpu_arm(args):
     # to move once -- N = uncompressed bytes, C = mean compressed bytes over the codec set
     cavg = csum / len(CODEC_SET)
     alg = {"k_enc_scan": n, "k_enc_auto": None, "k_enc_emit": 2 * cavg, "k_enc_copy_big": None,
-           "k_dec_map": cavg, "k_dec_compose": None, "k_dec_resolve": None, "k_dec_walk": cavg, "k_dec_scan": None,
-           "k_dec_expand": n + cavg}
+           "k_dec_map": cavg, "k_dec_compose": None, "k_dec_resolve": None, "k_dec_emit": n + cavg, "k_dec_big": None}
     name = top[0]
     alg_bytes = float(alg.get(name) or (n + cavg))     # state-only kernels are charged the whole call (N + C)
     avg_ms = top[1][1] / top[1][0]

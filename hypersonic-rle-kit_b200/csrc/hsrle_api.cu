@@ -135,8 +135,10 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   const size_t aggBytes = sp.K ? sizeof(DecAgg<7>) : sizeof(DecAgg<0>);
   // zero-initialised region first
   D.sc = cv.take<DecScalars>(1);
+  D.flagAgg = cv.take<uint32_t>((size_t)D.nSC + 1); D.flagInc = cv.take<uint32_t>((size_t)D.nSC + 1);
   if (zeroBytes) *zeroBytes = cv.off;
-  D.mbEntry = cv.take<uint16_t>((size_t)D.nSC * DEC_T);
+  D.medList = cv.take<DecBigOp>(((size_t)outSize >> 12) + 16);       // every deferred operation covers more than 4 KiB of output
+  D.hugeList = cv.take<DecBigOp>(((size_t)outSize >> 18) + 16);
   D.exTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
   D.finTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
   D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
@@ -275,8 +277,7 @@ static bool dec_prepare(int codec, const DecKernels *k)
   }
   if (g_dattrDone[codec]) return true;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
-  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->walkSmem), "attr walk")) return false;
-  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->expandSmem), "attr expand")) return false;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
   g_dattrDone[codec] = true;
   return true;
 }
@@ -298,9 +299,8 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DEC_T, k->mapSmem, st, D);
   HSRLE_LAUNCH(k_dec_compose, D.nSeg, DEC_WIN, DEC_SEG * DEC_WIN * 4, st, D);
   HSRLE_LAUNCH(k_dec_resolve, 1, D2B_T, 0, st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_walk", k->walk, D.nSC, DEC_T, k->walkSmem, st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_scan", k->scan, 1, D3S_T, 0, st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_expand", k->expand, D.nSC, DEC_T, k->expandSmem, st, D);
+  HSRLE_LAUNCH_NAMED("k_dec_emit", k->emit, D.nSC, DX_T, k->emitSmem, st, D);
+  HSRLE_LAUNCH_NAMED("k_dec_big", k->big, num_sms() * 4, 256, 0, st, D);
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }
 

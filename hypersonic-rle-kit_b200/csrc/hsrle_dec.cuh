@@ -59,6 +59,18 @@ struct DecScalars
   uint32_t singleSym;
   uint32_t endSeen;
   uint32_t nTok;
+  uint32_t ticket, done;                  // k_dec_emit: dynamic SC ids, CTAs finished
+  uint32_t emitBad;                       // k_dec_emit met an unparsable token on the true chain
+  uint32_t nHuge, nMed;                   // long operations handed to k_dec_big
+  unsigned long long outTotal;            // output bytes of all tokens
+};
+
+// a long literal copy (kind 0: src = stream position of the first byte) or run fill (kind 1: src = output position
+// where the run starts, sym = its first period) of nv whole 16-byte output vectors starting at vector v0
+struct DecBigOp
+{
+  uint32_t v0, nv, src, kind;
+  uint64_t sym;
 };
 
 // net effect of a token sequence on the K-entry LUT (decoder side)
@@ -157,8 +169,9 @@ struct DecBufs
   uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
   uint32_t *segEntry;       // [nSeg] true entry into the segment or POS_NONE
   uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
-  uint16_t *mbEntry;        // [nSC][DEC_T] entry of the true chain into every mini-block (0xFFFF: none)
-  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals, exclusive prefixes
+  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals; inclusive prefixes (last SC of every look-back group)
+  uint32_t *flagAgg, *flagInc;   // [nSC] "published" flags of the two (zeroed per call)
+  DecBigOp *medList, *hugeList;  // long operations for k_dec_big
   DecScalars *sc;
   uint32_t *dResult;
 };
@@ -167,6 +180,7 @@ struct DecBufs
 HSRLE_HD void dec_header(const Spec &sp, const uint8_t *in, uint32_t inSize, uint32_t outSize, DecScalars &sc)
 {
   sc.status = ST_OK; sc.single = 0; sc.singleSym = 0; sc.endSeen = 0; sc.nTok = 0; sc.n = 0; sc.clen = 0; sc.first = sp.hdr;
+  sc.ticket = 0; sc.done = 0; sc.emitBad = 0; sc.nHuge = 0; sc.nMed = 0; sc.outTotal = 0;
   if (inSize < (uint32_t)sp.hdr) { sc.status = ST_BADARG; return; }
   sc.n = load32(in); sc.clen = load32(in + 4);
   if (sc.n > outSize || sc.clen > inSize || sc.clen < (uint32_t)sp.hdr || sc.clen >= POS_SPECIAL) { sc.status = ST_BADARG; return; }

@@ -329,24 +329,88 @@ static __global__ void __launch_bounds__(D2B_T) k_dec_resolve(const DecBufs D)
 }
 
 // ================================================================================================
-// D3: token walk (D3a), scan over SCs (D3s), expansion (D3b)
-template <int K> struct DecWalkSmem
+// D3: k_dec_emit -- token walk, scan over the SCs (decoupled look-back), expansion; k_dec_big -- grid-wide long ops
+constexpr int DX_T = 256;                   // threads per SC (the first DEC_T of them walk one mini-block each)
+constexpr int DX_GROUP = DX_T;              // look-back group: aggregates of the group + inclusive prefix of the group before
+constexpr uint32_t DX_LONG_VECS = 256;      // literal copies / run fills of more 16-byte vectors than this are done by the whole CTA
+constexpr uint32_t DX_HUGE_VECS = 16384;    // ... and from here on (256 KiB) by the whole grid (k_dec_big)
+constexpr int DX_BIGCAP = 96;
+
+template <int K> struct DecEmitSmem
 {
-  alignas(16) uint8_t data[DEC_DATA_BYTES];  // skewed SC image
-  alignas(16) uint16_t ex[DEC_SCB];          // exit table from D1 (linear)
-  uint32_t mbEntry[DEC_T];                   // SC-relative entry of the true chain into every mini-block (or 0xFFFF)
-  DecAgg<K> warpAgg[DEC_T / 32];
-};
-template <int K> struct DecExpandSmem
-{
-  alignas(16) uint8_t data[DEC_DATA_BYTES];  // skewed SC image
-  alignas(16) uint64_t tSym[DEC_TOKCAP];     // token records of an expansion pass
-  uint32_t tOut[DEC_TOKCAP + 4];
-  uint32_t tLitLen[DEC_TOKCAP];
-  uint32_t tLitSrc[DEC_TOKCAP];
-  DecAgg<K> warpAgg[DEC_T / 32];
+  alignas(16) uint8_t data[DEC_DATA_BYTES];    // skewed SC image
+  union
+  {
+    alignas(16) uint16_t ex[DEC_SCB];          // exit table from D1 (linear), only needed to mark the chain
+    struct
+    {
+      uint64_t tSym[DEC_TOKCAP];               // token records of an expansion pass
+      uint32_t tOut[DEC_TOKCAP + 4];
+      uint32_t tLitLen[DEC_TOKCAP];
+      uint32_t tLitSrc[DEC_TOKCAP];
+    } rec;
+  } u;
+  uint32_t mbEntry[DEC_T];                     // SC-relative entry of the true chain into every mini-block (or 0xFFFF)
+  DecAgg<K> warpAgg[DX_T / 32];
+  DecAgg<K> bc;
+  DecBigOp big[DX_BIGCAP];
+  uint32_t nBig, ticket, flag;
 };
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
+{
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// field-wise helpers (K == 0 aggregates carry no LUT transform: nothing of it is moved)
+template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_up(const DecAgg<K> &v, int d)
+{
+  DecAgg<K> r;
+  r.out = __shfl_up_sync(0xFFFFFFFFu, v.out, d);
+  r.ntok = __shfl_up_sync(0xFFFFFFFFu, v.ntok, d);
+  r.has = __shfl_up_sync(0xFFFFFFFFu, v.has, d);
+  r.sym = __shfl_up_sync(0xFFFFFFFFu, v.sym, d);
+  if (K)
+  {
+    uint64_t refs = 0;
+#pragma unroll
+    for (int i = 0; i < 7; i++) if (i < K) { r.xf.sym[i] = __shfl_up_sync(0xFFFFFFFFu, v.xf.sym[i], d); refs |= (uint64_t)(uint8_t)v.xf.ref[i] << (8 * i); }
+    refs = __shfl_up_sync(0xFFFFFFFFu, refs, d);
+#pragma unroll
+    for (int i = 0; i < 7; i++) if (i < K) r.xf.ref[i] = (int8_t)(refs >> (8 * i));
+  }
+  return r;
+}
+template <int K> __device__ __forceinline__ void decagg_store(DecAgg<K> *dst, const DecAgg<K> &v)
+{
+  dst->out = v.out; dst->ntok = v.ntok; dst->has = v.has; dst->sym = v.sym;
+  if (K)
+  {
+#pragma unroll
+    for (int i = 0; i < 7; i++) if (i < K) { dst->xf.sym[i] = v.xf.sym[i]; dst->xf.ref[i] = v.xf.ref[i]; }
+  }
+}
+// L2 loads (the aggregates are written by other CTAs while this kernel runs: never through the non-coherent L1)
+template <int K> __device__ __forceinline__ DecAgg<K> decagg_load_cg(const DecAgg<K> *src)
+{
+  DecAgg<K> r = decagg_identity<K>();
+  r.out = __ldcg(&src->out); r.ntok = __ldcg(&src->ntok); r.has = __ldcg(&src->has); r.sym = __ldcg(&src->sym);
+  if (K)
+  {
+    const unsigned long long refs = __ldcg(reinterpret_cast<const unsigned long long *>(src->xf.ref));
+#pragma unroll
+    for (int i = 0; i < 7; i++) if (i < K) { r.xf.sym[i] = __ldcg(&src->xf.sym[i]); r.xf.ref[i] = (int8_t)(refs >> (8 * i)); }
+  }
+  return r;
+}
+
+// exclusive scan over the CTA in thread order; total = combination of everything
 template <int K> __device__ __forceinline__ DecAgg<K> dec_block_excl_scan(DecAgg<K> *warpBuf, const DecAgg<K> &mine, DecAgg<K> &total)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,11 +419,11 @@ template <int K> __device__ __forceinline__ DecAgg<K> dec_block_excl_scan(DecAgg
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1)
   {
-    const DecAgg<K> o = shfl_up_t(inc, d);
+    const DecAgg<K> o = decagg_shfl_up<K>(inc, d);
     if (lane >= d) inc = decagg_combine<K>(o, inc);
   }
-  if (lane == 31) warpBuf[warp] = inc;
-  DecAgg<K> ex = shfl_up_t(inc, 1);
+  if (lane == 31) decagg_store<K>(&warpBuf[warp], inc);
+  DecAgg<K> ex = decagg_shfl_up<K>(inc, 1);
   if (lane == 0) ex = decagg_identity<K>();
   __syncthreads();
   DecAgg<K> pre = decagg_identity<K>();
@@ -401,94 +465,6 @@ __device__ __forceinline__ void dec_walk_sizes(const uint8_t *data, uint32_t myE
   }
 }
 
-// D3a: per SC, mark the true chain (entries into the mini-blocks) and total its tokens
-template <int W, int BA, int V>
-__global__ void __launch_bounds__(DEC_T) k_dec_walk(const DecBufs D)
-{
-  constexpr Spec sp = make_spec(W, BA, V);
-  constexpr int K = sp.K;
-  using Agg = DecAgg<K>;
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  DecWalkSmem<K> &S = *reinterpret_cast<DecWalkSmem<K> *>(smemRaw);
-  const DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;
-  const uint32_t c = blockIdx.x, c0 = c * DEC_SCB, clen = sc.clen;
-  const bool single = sc.single != 0;
-  const int t = threadIdx.x;
-  Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf);
-  const uint32_t entry = D.scEntry[c];
-  if (entry >= POS_SPECIAL)
-  { // no token starts here
-    if (t == 0) aggBuf[c] = decagg_identity<K>();
-    D.mbEntry[(size_t)c * DEC_T + t] = 0xFFFFu;
-    return;
-  }
-  dec_load_sc(S.data, D.in, c0, clen);
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(D.exTab + (size_t)c * DEC_SCB);
-    uint4 *dst = reinterpret_cast<uint4 *>(S.ex);
-    for (uint32_t v = t; v < DEC_SCB * 2 / 16; v += DEC_T) dst[v] = __ldg(src + v);
-  }
-  S.mbEntry[t] = 0xFFFFu;
-  __syncthreads();
-  if (t == 0)
-  {
-    uint32_t p = entry - c0;
-    while (p < DEC_SCB)
-    {
-      S.mbEntry[p / DEC_MB] = p;
-      const uint32_t code = S.ex[p];
-      p = code < EX_FAR ? code : DEC_SCB;          // leaves the SC (or ends / breaks inside this mini-block)
-    }
-  }
-  __syncthreads();
-  const uint32_t myEntry = S.mbEntry[t];
-  D.mbEntry[(size_t)c * DEC_T + t] = (uint16_t)myEntry;
-  Agg mine = decagg_identity<K>();
-  bool sawEnd = false, sawBad = false;
-  if (myEntry != 0xFFFFu) dec_walk_sizes<W, BA, V>(S.data, myEntry, c0, clen, single, mine, sawEnd, sawBad);
-  if (__syncthreads_or(sawBad ? 1 : 0)) { if (t == 0) D.sc->status = ST_BADSTREAM; }
-  if (__syncthreads_or(sawEnd ? 1 : 0)) { if (t == 0) D.sc->endSeen = 1; }
-  Agg total;
-  (void)dec_block_excl_scan<K>(S.warpAgg, mine, total);
-  if (t == 0) aggBuf[c] = total;
-}
-
-// D3s: exclusive scan of the SC aggregates (one CTA); final status and result
-constexpr int D3S_T = 1024;
-template <int K>
-__global__ void __launch_bounds__(D3S_T) k_dec_scan(const DecBufs D)
-{
-  using Agg = DecAgg<K>;
-  __shared__ Agg warpAgg[D3S_T / 32];
-  DecScalars &sc = *D.sc;
-  const int t = threadIdx.x;
-  Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
-  if (sc.status == ST_OK)
-  {
-    const uint32_t nSC = D.nSC;
-    const uint32_t per = (nSC + D3S_T - 1) / D3S_T;
-    const uint32_t lo = min(nSC, (uint32_t)t * per), hi = min(nSC, lo + per);
-    Agg mine = decagg_identity<K>();
-    for (uint32_t c = lo; c < hi; c++) mine = decagg_combine<K>(mine, aggBuf[c]);
-    Agg total;
-    Agg run = dec_block_excl_scan<K>(warpAgg, mine, total);
-    for (uint32_t c = lo; c < hi; c++) { const Agg a = aggBuf[c]; incBuf[c] = run; run = decagg_combine<K>(run, a); }   // incBuf = EXCLUSIVE prefix
-    if (t == 0)
-    {
-      sc.nTok = total.ntok;
-      if (!sc.endSeen || total.out != (uint64_t)sc.n) sc.status = ST_BADSTREAM;
-    }
-  }
-  __syncthreads();
-  if (t == 0)
-  {
-    const uint32_t status = sc.status;
-    D.dResult[0] = status == ST_OK ? sc.n : 0; D.dResult[1] = status; D.dResult[2] = sc.nTok; D.dResult[3] = D.nSC;
-    D.dResult[4] = sc.clen; D.dResult[5] = sc.single; D.dResult[6] = 0; D.dResult[7] = 0;
-  }
-}
-
 // symbol of a token given the running symbol state; updates the state
 template <int W, int BA, int V>
 __device__ __forceinline__ uint64_t dec_token_symbol(const Tok &t, const SkewReader &rd, uint64_t &symReg, Lut &lut)
@@ -506,35 +482,153 @@ __device__ __forceinline__ uint64_t dec_token_symbol(const Tok &t, const SkewRea
   return symReg;
 }
 
-// D3b: expansion.  Per SC: token records (output offset, literal source, symbol) in passes of DEC_TOKCAP
-// tokens, then one 16-byte aligned output vector per thread and step.
+// ---- 16-byte output vectors
+// stream bytes [src, src+16) (any alignment; only aligned words holding at least one of them are read)
+__device__ __forceinline__ uint4 dec_lit_vec(const uint8_t *__restrict__ in, uint32_t src)
+{
+  const uint32_t sb = src & 3u;
+  const uint32_t *sw = reinterpret_cast<const uint32_t *>(in + (src - sb));
+  const uint32_t w0 = __ldg(sw), w1 = __ldg(sw + 1), w2 = __ldg(sw + 2), w3 = __ldg(sw + 3);
+  if (sb == 0) return make_uint4(w0, w1, w2, w3);
+  const uint32_t w4 = __ldg(sw + 4), sh = sb * 8;
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// 16 bytes of the period-W pattern `sym` starting at pattern offset ph (0 <= ph < W)
+template <int W> __device__ __forceinline__ uint4 dec_run_vec(uint64_t sym, uint32_t ph)
+{
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) w[j] = pattern_word(sym, W, (ph + 4 * j) % W);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <int W> __device__ __forceinline__ void dec_big_vec(const DecBigOp &op, uint32_t k, const uint8_t *__restrict__ in, uint8_t *__restrict__ out)
+{ // vector k of a long operation
+  const uint32_t v = op.v0 + k;
+  uint4 x;
+  if (op.kind == 0) x = dec_lit_vec(in, op.src + 16u * k);
+  else x = dec_run_vec<W>(op.sym, (uint32_t)(((uint64_t)v * 16 - op.src) % (uint32_t)W));
+  *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = x;
+}
+
+// the CTA's last act: the last CTA of the grid settles the status and the result
+__device__ __forceinline__ void dec_emit_done(const DecBufs &D, uint32_t *flagSlot)
+{
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    *flagSlot = (atomicAdd(&D.sc->done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    if (*flagSlot)
+    {
+      __threadfence();
+      DecScalars &sc = *D.sc;
+      uint32_t status = ld_volatile_u32(&sc.status);
+      if (status == ST_OK)
+      {
+        const uint32_t bad = ld_volatile_u32(&sc.emitBad), end = ld_volatile_u32(&sc.endSeen);
+        const unsigned long long tot = ld_volatile_u64(&sc.outTotal);
+        if (bad || !end || tot != (unsigned long long)sc.n) { status = ST_BADSTREAM; sc.status = status; }
+      }
+      D.dResult[0] = status == ST_OK ? sc.n : 0; D.dResult[1] = status; D.dResult[2] = ld_volatile_u32(&sc.nTok); D.dResult[3] = D.nSC;
+      D.dResult[4] = sc.clen; D.dResult[5] = sc.single; D.dResult[6] = ld_volatile_u32(&sc.nHuge); D.dResult[7] = 0;
+    }
+  }
+}
+
 template <int W, int BA, int V>
-__global__ void __launch_bounds__(DEC_T) k_dec_expand(const DecBufs D)
+__global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
 {
   constexpr Spec sp = make_spec(W, BA, V);
   constexpr int K = sp.K;
   using Agg = DecAgg<K>;
-  using Smem = DecExpandSmem<K>;
+  using Smem = DecEmitSmem<K>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
-  const DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;
-  const uint32_t c = blockIdx.x, c0 = c * DEC_SCB;
+  DecScalars &sc = *D.sc;
+  const int t = threadIdx.x;
+  // status as the kernels before left it: uniform over the grid (errors found here go to sc.emitBad)
+  if (sc.status != ST_OK) { dec_emit_done(D, &S.flag); return; }
+  if (t == 0) { S.ticket = atomicAdd(&sc.ticket, 1u); S.nBig = 0; }
+  __syncthreads();
+  const uint32_t c = S.ticket, c0 = c * DEC_SCB;
   const uint32_t clen = sc.clen, n = sc.n;
   const bool single = sc.single != 0;
-  const int t = threadIdx.x;
-  const Agg *aggBuf = reinterpret_cast<const Agg *>(D.aggBuf), *exclBuf = reinterpret_cast<const Agg *>(D.incBuf);
-  if (D.scEntry[c] >= POS_SPECIAL) return;
-  const Agg total = aggBuf[c];
-  if (total.ntok == 0) return;
-  const Agg exclusive = exclBuf[c];
-  dec_load_sc(S.data, D.in, c0, clen);
-  const uint32_t myEntry = D.mbEntry[(size_t)c * DEC_T + t];
-  __syncthreads();
+  Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
+  const uint32_t entry = D.scEntry[c];
+  const bool hasTok = entry < POS_SPECIAL;
+
+  // ---- the SC's tokens: chain marks, walk #1
   Agg mine = decagg_identity<K>();
-  { bool e = false, b = false; if (myEntry != 0xFFFFu) dec_walk_sizes<W, BA, V>(S.data, myEntry, c0, clen, single, mine, e, b); }
-  Agg totalChk;
-  const Agg pre = dec_block_excl_scan<K>(S.warpAgg, mine, totalChk);
+  uint32_t myEntry = 0xFFFFu;
+  if (hasTok)
+  {
+    dec_load_sc(S.data, D.in, c0, clen);
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(D.exTab + (size_t)c * DEC_SCB);
+      uint4 *dst = reinterpret_cast<uint4 *>(S.u.ex);
+      for (uint32_t v = t; v < DEC_SCB * 2 / 16; v += DX_T) dst[v] = __ldg(src + v);
+    }
+    if (t < DEC_T) S.mbEntry[t] = 0xFFFFu;
+    __syncthreads();
+    if (t == 0)
+    {
+      uint32_t p = entry - c0;
+      while (p < DEC_SCB)
+      {
+        S.mbEntry[p / DEC_MB] = p;
+        const uint32_t code = S.u.ex[p];
+        p = code < EX_FAR ? code : DEC_SCB;          // leaves the SC (or ends / breaks inside this mini-block)
+      }
+    }
+    __syncthreads();
+    bool sawEnd = false, sawBad = false;
+    if (t < DEC_T)
+    {
+      myEntry = S.mbEntry[t];
+      if (myEntry != 0xFFFFu) dec_walk_sizes<W, BA, V>(S.data, myEntry, c0, clen, single, mine, sawEnd, sawBad);
+    }
+    if (sawBad) sc.emitBad = 1;
+    if (sawEnd) sc.endSeen = 1;
+  }
+  Agg total;
+  const Agg pre = dec_block_excl_scan<K>(S.warpAgg, mine, total);
+
+  // ---- scan over the SCs: publish my aggregate, gather the group's aggregates and the prefix of the group before
+  if (t == 0) { decagg_store<K>(&aggBuf[c], total); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
+  const uint32_t g0 = (c / DX_GROUP) * DX_GROUP;
+  Agg part = decagg_identity<K>();
+  {
+    const uint32_t p = g0 + t;
+    if (p < c)
+    {
+      while (ld_volatile_u32(D.flagAgg + p) == 0u) { }
+      __threadfence();
+      part = decagg_load_cg<K>(&aggBuf[p]);
+    }
+  }
+  Agg exclusive;
+  (void)dec_block_excl_scan<K>(S.warpAgg, part, exclusive);
+  if (g0 > 0)
+  {
+    if (t == 0)
+    {
+      while (ld_volatile_u32(D.flagInc + (g0 - 1)) == 0u) { }
+      __threadfence();
+      const Agg before = decagg_load_cg<K>(&incBuf[g0 - 1]);
+      decagg_store<K>(&S.bc, before);
+    }
+    __syncthreads();
+    const Agg before = S.bc;
+    exclusive = decagg_combine<K>(before, exclusive);
+  }
+  const bool lastOfGrid = c == gridDim.x - 1;
+  if (t == 0 && ((c % DX_GROUP) == DX_GROUP - 1 || lastOfGrid))
+  {
+    const Agg inclusive = decagg_combine<K>(exclusive, total);
+    decagg_store<K>(&incBuf[c], inclusive); __threadfence(); st_volatile_u32(D.flagInc + c, 1u);
+    if (lastOfGrid) { st_volatile_u64(&sc.outTotal, inclusive.out); st_volatile_u32(&sc.nTok, inclusive.ntok); }
+  }
+  if (!hasTok || total.ntok == 0) { dec_emit_done(D, &S.flag); return; }
 
   // ---- state at the start of my mini-block
   const Agg before = decagg_combine<K>(exclusive, pre);
@@ -543,8 +637,10 @@ __global__ void __launch_bounds__(DEC_T) k_dec_expand(const DecBufs D)
   if (K) { Lut l0 = lut; lutxf_apply(before.xf, K, l0, lut); }
   uint64_t outPos = before.out;
   const uint64_t scOut1 = exclusive.out + total.out;
-  uint64_t *tSym = S.tSym;
-  uint32_t *tOut = S.tOut, *tLitLen = S.tLitLen, *tLitSrc = S.tLitSrc;
+  uint64_t *tSym = S.u.rec.tSym;
+  uint32_t *tOut = S.u.rec.tOut, *tLitLen = S.u.rec.tLitLen, *tLitSrc = S.u.rec.tLitSrc;
+  const uint8_t *__restrict__ in = D.in;
+  uint8_t *__restrict__ out = D.out;
 
   // ---- expansion in passes of DEC_TOKCAP tokens
   uint32_t p = myEntry == 0xFFFFu ? DEC_SCB : myEntry;
@@ -553,74 +649,164 @@ __global__ void __launch_bounds__(DEC_T) k_dec_expand(const DecBufs D)
   for (uint32_t pass0 = 0; pass0 < total.ntok; pass0 += DEC_TOKCAP)
   {
     const uint32_t passN = min(DEC_TOKCAP, total.ntok - pass0);
-    __syncthreads();
-    while (p < b1 && k < pass0 + passN)
+    __syncthreads();                                                   // the exit table / the previous pass's records are dead
+    if (t < DEC_T)
     {
-      SkewReader rd; rd.data = S.data; rd.p = p;
-      Tok tk; dec_parse_rd(sp, single, rd, (uint64_t)clen - (c0 + p), tk);
-      if (!tk.valid) { p = DEC_SCB; break; }
-      const uint64_t sym = dec_token_symbol<W, BA, V>(tk, rd, symReg, lut);
-      const uint32_t r = k - pass0;
-      tOut[r] = (uint32_t)outPos; tLitLen[r] = tk.litLen; tLitSrc[r] = c0 + p + tk.hdrLen; tSym[r] = sym;
-      outPos += (uint64_t)tk.litLen + tk.runLen; k++;
-      if (tk.last) { p = DEC_SCB; break; }
-      const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
-      p = nx < DEC_SCB ? (uint32_t)nx : DEC_SCB;
-    }
-    // sentinel: start of the first token of the next pass (written by its owner), or the end of the SC's output
-    if (k == pass0 + passN && p < b1 && pass0 + passN < total.ntok) tOut[passN] = (uint32_t)outPos;
-    if (pass0 + passN >= total.ntok && t == 0) tOut[passN] = (uint32_t)min(scOut1, (uint64_t)0xFFFFFFFFu);
-    __syncthreads();
-    const uint64_t o0 = tOut[0];
-    const uint64_t oEnd = min((uint64_t)tOut[passN], (uint64_t)n);      // never write beyond the declared size
-    if (o0 >= oEnd) continue;
-    const uint64_t v0 = o0 >> 4, v1 = (oEnd + 15) >> 4;
-    for (uint64_t v = v0 + t; v < v1; v += DEC_T)
-    {
-      const uint64_t vb = v << 4;
-      const uint64_t lo = max(vb, o0), hi = min(vb + 16, oEnd);
-      // token covering lo: largest r with tOut[r] <= lo
-      uint32_t a = 0, b = passN - 1;
-      while (a < b) { const uint32_t m = (a + b + 1) >> 1; if (tOut[m] <= lo) a = m; else b = m - 1; }
-      uint32_t r = a;
-      uint64_t tStart = tOut[r], tNext = tOut[r + 1];
-      uint32_t litLen = tLitLen[r];
-      uint32_t w4[4] = { 0, 0, 0, 0 };
-      // fast path: the whole vector lies inside one run
-      if (lo == vb && hi == vb + 16 && lo >= tStart + litLen && vb + 16 <= tNext)
+      while (p < b1 && k < pass0 + passN)
       {
-        const uint64_t sym = tSym[r];
-        const uint32_t ph = (uint32_t)(lo - (tStart + litLen)) % (uint32_t)W;
-#pragma unroll
-        for (int j = 0; j < 4; j++) w4[j] = pattern_word(sym, W, (ph + 4 * j) % W);
+        SkewReader rd; rd.data = S.data; rd.p = p;
+        Tok tk; dec_parse_rd(sp, single, rd, (uint64_t)clen - (c0 + p), tk);
+        if (!tk.valid) { p = DEC_SCB; break; }
+        const uint64_t sym = dec_token_symbol<W, BA, V>(tk, rd, symReg, lut);
+        const uint32_t r = k - pass0;
+        tOut[r] = (uint32_t)min(outPos, (uint64_t)n); tLitLen[r] = tk.litLen; tLitSrc[r] = c0 + p + tk.hdrLen; tSym[r] = sym;
+        outPos += (uint64_t)tk.litLen + tk.runLen; k++;
+        if (tk.last) { p = DEC_SCB; break; }
+        const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
+        p = nx < DEC_SCB ? (uint32_t)nx : DEC_SCB;
       }
+      // sentinel: start of the first token of the next pass (written by its owner), or the end of the SC's output
+      if (k == pass0 + passN && p < b1 && pass0 + passN < total.ntok) tOut[passN] = (uint32_t)min(outPos, (uint64_t)n);
+      if (pass0 + passN >= total.ntok && t == 0) tOut[passN] = (uint32_t)min(scOut1, (uint64_t)n);   // never write beyond the declared size
+    }
+    __syncthreads();
+    const uint32_t pStart = tOut[0], pEnd = tOut[passN];
+    if (pStart >= pEnd) continue;
+
+    // -- phase M: vectors that mix segments (literal / run of neighbouring tokens), one owning token per thread;
+    //    item passN is the partial vector at the start of the pass (its first bytes belong to the pass / SC before)
+    for (uint32_t r = t; r <= passN; r += DX_T)
+    {
+      uint32_t vbs[2]; int nvb = 0; uint32_t r0 = r;
+      if (r == passN) { if (pStart & 15u) vbs[nvb++] = pStart & ~15u; r0 = 0; }
       else
       {
+        const uint32_t o = tOut[r], o1 = tOut[r + 1];
+        const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
+        if (m > o && (m & 15u) && (m & ~15u) >= o) vbs[nvb++] = m & ~15u;
+        if (o1 > m && (o1 & 15u) && (o1 & ~15u) >= m) vbs[nvb++] = o1 & ~15u;
+      }
+      for (int q = 0; q < nvb; q++)
+      {
+        const uint64_t vb = vbs[q];
+        const uint64_t lo = max(vb, (uint64_t)pStart), hi = min(vb + 16, (uint64_t)pEnd);
+        uint32_t rr = r0;
+        uint64_t tStart = tOut[rr], tNext = tOut[rr + 1];
+        uint32_t litLen = tLitLen[rr];
+        uint32_t w4[4] = { 0, 0, 0, 0 };
 #pragma unroll
         for (int i = 0; i < 16; i++)
         {
-          const uint64_t q = vb + i;
-          if (q >= lo && q < hi)
+          const uint64_t x = vb + i;
+          if (x >= lo && x < hi)
           {
-            while (q >= tNext) { r++; tStart = tNext; tNext = tOut[r + 1]; litLen = tLitLen[r]; }
+            while (x >= tNext) { rr++; tStart = tNext; tNext = tOut[rr + 1]; litLen = tLitLen[rr]; }
             const uint64_t litEnd = tStart + litLen;
             uint32_t byte;
-            if (q < litEnd)
+            if (x < litEnd)
             {
-              const uint32_t sp_ = tLitSrc[r] + (uint32_t)(q - tStart);
-              byte = (sp_ - c0 < DEC_SCB + DEC_PAD) ? S.data[skew8(sp_ - c0)] : __ldg(D.in + sp_);
+              const uint32_t sp_ = tLitSrc[rr] + (uint32_t)(x - tStart);
+              byte = (sp_ - c0 < DEC_SCB + DEC_PAD) ? S.data[skew8(sp_ - c0)] : __ldg(in + sp_);
             }
             else
             {
-              const uint32_t ph = (uint32_t)(q - litEnd) % (uint32_t)W;
-              byte = (uint32_t)(tSym[r] >> (8 * ph)) & 0xFFu;
+              const uint32_t ph = (uint32_t)(x - litEnd) % (uint32_t)W;
+              byte = (uint32_t)(tSym[rr] >> (8 * ph)) & 0xFFu;
             }
             w4[i >> 2] |= byte << (8 * (i & 3));
           }
         }
+        if (lo == vb && hi == vb + 16) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        else for (uint64_t x = lo; x < hi; x++) out[x] = (uint8_t)(w4[(x - vb) >> 2] >> (8 * ((x - vb) & 3)));
       }
-      if (lo == vb && hi == vb + 16) *reinterpret_cast<uint4 *>(D.out + vb) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-      else for (uint64_t q = lo; q < hi; q++) D.out[q] = (uint8_t)(w4[(q - vb) >> 2] >> (8 * ((q - vb) & 3)));
+    }
+
+    // -- phase F: vectors inside one literal / one run, eight lanes per token; long ones are deferred
+    {
+      auto defer = [&](const DecBigOp &op)
+      {
+        if (op.nv >= DX_HUGE_VECS) { D.hugeList[atomicAdd(&sc.nHuge, 1u)] = op; return; }
+        const uint32_t slot = atomicAdd(&S.nBig, 1u);
+        if (slot < (uint32_t)DX_BIGCAP) S.big[slot] = op;
+        else D.medList[atomicAdd(&sc.nMed, 1u)] = op;        // more long operations than the CTA's list holds: k_dec_big
+      };
+      const int grp = t >> 3, l8 = t & 7;
+      for (uint32_t r = grp; r < passN; r += DX_T / 8)
+      {
+        const uint32_t o = tOut[r], o1 = tOut[r + 1];
+        const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
+        { // literal: vectors [ceil(o/16), floor(m/16))
+          const uint32_t v0 = (o >> 4) + ((o & 15u) ? 1u : 0u), v1 = m >> 4;
+          if (v1 > v0)
+          {
+            const uint32_t src0 = tLitSrc[r] + (v0 * 16u - o);
+            if (v1 - v0 > DX_LONG_VECS)
+            {
+              if (l8 == 0)
+              {
+                DecBigOp op; op.v0 = v0; op.nv = v1 - v0; op.src = src0; op.kind = 0; op.sym = 0;
+                defer(op);
+              }
+            }
+            else for (uint32_t v = v0 + l8; v < v1; v += 8) *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = dec_lit_vec(in, src0 + (v - v0) * 16u);
+          }
+        }
+        { // run: vectors [ceil(m/16), floor(o1/16))
+          const uint32_t v0 = (m >> 4) + ((m & 15u) ? 1u : 0u), v1 = o1 >> 4;
+          if (v1 > v0)
+          {
+            const uint64_t sym = tSym[r];
+            if (v1 - v0 > DX_LONG_VECS)
+            {
+              if (l8 == 0)
+              {
+                DecBigOp op; op.v0 = v0; op.nv = v1 - v0; op.src = m; op.kind = 1; op.sym = sym;
+                defer(op);
+              }
+            }
+            else for (uint32_t v = v0 + l8; v < v1; v += 8) *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = dec_run_vec<W>(sym, (v * 16u - m) % (uint32_t)W);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // -- long operations: the whole CTA, or (huge) the whole grid in k_dec_big
+    {
+      const uint32_t nb = min(S.nBig, (uint32_t)DX_BIGCAP);
+      for (uint32_t i = 0; i < nb; i++)
+      {
+        const DecBigOp op = S.big[i];
+        for (uint32_t kk = t; kk < op.nv; kk += DX_T) dec_big_vec<W>(op, kk, in, out);
+      }
+      __syncthreads();
+      if (t == 0) S.nBig = 0;
+    }
+  }
+  dec_emit_done(D, &S.flag);
+}
+
+// grid-wide execution of the huge literal copies / run fills (a 1 GiB single-symbol frame is ONE run)
+constexpr uint32_t DBIG_PIECE = 1024;      // vectors per CTA step (16 KiB)
+template <int W>
+__global__ void __launch_bounds__(256) k_dec_big(const DecBufs D)
+{
+  const DecScalars &sc = *D.sc;
+  if (sc.status != ST_OK) return;
+  const uint32_t nMed = sc.nMed;
+  for (uint32_t i = blockIdx.x; i < nMed; i += gridDim.x)
+  {
+    const DecBigOp op = D.medList[i];
+    for (uint32_t kk = threadIdx.x; kk < op.nv; kk += 256) dec_big_vec<W>(op, kk, D.in, D.out);
+  }
+  const uint32_t nHuge = sc.nHuge;
+  for (uint32_t i = 0; i < nHuge; i++)
+  {
+    const DecBigOp op = D.hugeList[i];
+    const uint32_t nPieces = (op.nv + DBIG_PIECE - 1) / DBIG_PIECE;
+    for (uint32_t pc = blockIdx.x; pc < nPieces; pc += gridDim.x)
+    {
+      const uint32_t k0 = pc * DBIG_PIECE, k1 = min(op.nv, k0 + DBIG_PIECE);
+      for (uint32_t kk = k0 + threadIdx.x; kk < k1; kk += 256) dec_big_vec<W>(op, kk, D.in, D.out);
     }
   }
 }

@@ -20,10 +20,9 @@ struct EncKernels
 struct DecKernels
 {
   void (*map)(const DecBufs);
-  void (*walk)(const DecBufs);
-  void (*scan)(const DecBufs);
-  void (*expand)(const DecBufs);
-  size_t mapSmem, walkSmem, expandSmem;
+  void (*emit)(const DecBufs);
+  void (*big)(const DecBufs);
+  size_t mapSmem, emitSmem;
   size_t aggBytes;        // sizeof(DecAgg<K>)
 };
 

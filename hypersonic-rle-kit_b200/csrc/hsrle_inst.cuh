@@ -27,12 +27,10 @@ template <int W, int BA, int V> static DecKernels make_dec_kernels()
   constexpr Spec sp = make_spec(W, BA, V);
   DecKernels k;
   k.map = &k_dec_map<W, BA, V>;
-  k.walk = &k_dec_walk<W, BA, V>;
-  k.scan = &k_dec_scan<sp.K>;
-  k.expand = &k_dec_expand<W, BA, V>;
-  k.walkSmem = sizeof(DecWalkSmem<sp.K>);
+  k.emit = &k_dec_emit<W, BA, V>;
+  k.big = &k_dec_big<W>;
   k.mapSmem = sizeof(DecMapSmem);
-  k.expandSmem = sizeof(DecExpandSmem<sp.K>);
+  k.emitSmem = sizeof(DecEmitSmem<sp.K>);
   k.aggBytes = sizeof(DecAgg<sp.K>);
   return k;
 }
@@ -66,7 +64,7 @@ const DecKernels *HSRLE_CAT(dec_kernels_w, HSRLE_INST_W)()
   static bool init = false;
   if (!init)
   {
-    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0 };
+    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, 0, 0, 0 };
     constexpr int W = HSRLE_INST_W;
     if constexpr (W > 1)
     {
