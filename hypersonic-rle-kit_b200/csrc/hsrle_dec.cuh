@@ -73,63 +73,79 @@ struct DecBigOp
   uint64_t sym;
 };
 
-// net effect of a token sequence on the K-entry LUT (decoder side)
+// net effect of a token sequence on the K-entry LUT (decoder side): entry i of the table afterwards is either the
+// incoming entry e[i] (e[i] < 8) or the symbol stored in the stream at position e[i] (>= 8: symbols follow a token
+// head, which follows the stream header).  Symbols are fetched only when a transform is applied to a table.
 struct LutXf
 {
-  uint64_t sym[7];
-  int8_t ref[8];        // >=0: incoming entry ref[i]; -1: explicit sym[i]
+  uint32_t e[7];
+  uint32_t pad;
 };
 HSRLE_HD void lutxf_identity(LutXf &x)
 {
   HSRLE_UNROLL
-  for (int i = 0; i < 7; i++) { x.ref[i] = (int8_t)i; x.sym[i] = 0; }
-  x.ref[7] = 0;
+  for (int i = 0; i < 7; i++) x.e[i] = (uint32_t)i;
+  x.pad = 0;
 }
 // (static indices only: see the LUT helpers in hsrle_core.cuh)
-HSRLE_HD void lutxf_touch(LutXf &x, int K, int idx, uint64_t sym)
-{ // idx<K: move entry idx to front; idx==K: push explicit symbol
+HSRLE_HD void lutxf_touch(LutXf &x, int K, int idx, uint32_t symPos)
+{ // idx<K: move entry idx to front; idx==K: push the explicit symbol stored at symPos
   if (idx == 0) return;
-  uint64_t s0 = sym; int8_t r0 = -1;
+  uint32_t e0 = symPos;
   int from = K - 1;
   if (idx != K)
   {
     from = idx;
     HSRLE_UNROLL
-    for (int i = 1; i < 7; i++) if (i < K && i == idx) { s0 = x.sym[i]; r0 = x.ref[i]; }
+    for (int i = 1; i < 7; i++) if (i < K && i == idx) e0 = x.e[i];
   }
   HSRLE_UNROLL
-  for (int j = 6; j > 0; j--) if (j < K && j <= from) { x.sym[j] = x.sym[j - 1]; x.ref[j] = x.ref[j - 1]; }
-  x.sym[0] = s0; x.ref[0] = r0;
+  for (int j = 6; j > 0; j--) if (j < K && j <= from) x.e[j] = x.e[j - 1];
+  x.e[0] = e0;
+}
+// key == j ? a : b.  On the device this is an opaque setp/selp pair: left to itself the compiler turns the unrolled
+// select chains below into dynamically indexed local-memory arrays.
+HSRLE_HD uint32_t sel_eq_u32(uint32_t key, uint32_t j, uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+  uint32_t r;
+  asm("{ .reg .pred p; setp.eq.u32 p, %1, %2; selp.u32 %0, %3, %4, p; }" : "=r"(r) : "r"(key), "r"(j), "r"(a), "r"(b));
+  return r;
+#else
+  return key == j ? a : b;
+#endif
+}
+HSRLE_HD uint64_t sel_eq_u64(uint32_t key, uint32_t j, uint64_t a, uint64_t b)
+{
+  return (uint64_t)sel_eq_u32(key, j, (uint32_t)a, (uint32_t)b) | ((uint64_t)sel_eq_u32(key, j, (uint32_t)(a >> 32), (uint32_t)(b >> 32)) << 32);
 }
 HSRLE_HD LutXf lutxf_compose(const LutXf &older, const LutXf &newer, int K)
 {
-  LutXf r; r.ref[7] = 0;
+  LutXf r; r.pad = 0;
   HSRLE_UNROLL
   for (int i = 0; i < 7; i++)
   {
-    r.sym[i] = 0; r.ref[i] = (int8_t)i;
+    uint32_t v = newer.e[i];
     if (i < K)
     {
-      if (newer.ref[i] < 0) { r.sym[i] = newer.sym[i]; r.ref[i] = -1; }
-      else
-      {
-        HSRLE_UNROLL
-        for (int j = 0; j < 7; j++) if (j < K && newer.ref[i] == j) { r.sym[i] = older.sym[j]; r.ref[i] = older.ref[j]; }
-      }
+      HSRLE_UNROLL
+      for (int j = 0; j < 7; j++) if (j < K) v = sel_eq_u32(newer.e[i], (uint32_t)j, older.e[j], v);
     }
+    r.e[i] = v;
   }
   return r;
 }
-HSRLE_HD void lutxf_apply(const LutXf &x, int K, const Lut &in, Lut &out)
+HSRLE_HD void lutxf_apply(const LutXf &x, int K, int W, const uint8_t *stream, const Lut &in, Lut &out)
 {
   HSRLE_UNROLL
   for (int i = 0; i < 7; i++)
   {
     if (i < K)
     {
-      uint64_t v = x.sym[i];
+      uint64_t v = 0;
+      if (x.e[i] >= 8u) v = load_sym(stream + x.e[i], W);
       HSRLE_UNROLL
-      for (int j = 0; j < 7; j++) if (j < K && x.ref[i] == j) v = in.s[j];
+      for (int j = 0; j < 7; j++) if (j < K) v = sel_eq_u64(x.e[i], (uint32_t)j, in.s[j], v);
       out.s[i] = v;
     }
   }

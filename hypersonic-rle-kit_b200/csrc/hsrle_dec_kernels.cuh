@@ -140,7 +140,7 @@ __device__ __forceinline__ uint64_t toklen(const TokWin &x, bool single, uint64_
 // ex[q] (u16, SC-relative): < EX_FAR: where the chain that starts at q leaves q's mini-block; EX_FAR | q': the
 // token at q' jumps beyond c0 + 0x7FFF; EX_END / EX_BAD.
 template <int W, int BA, int V>
-__device__ __forceinline__ void dec_sweep(const uint8_t *data, uint16_t *ex, uint32_t c0, uint32_t clen, bool single)
+__device__ __forceinline__ void dec_sweep(const uint8_t *data, uint16_t *ex, uint32_t *fin, uint32_t c0, uint32_t clen, bool single)
 {
   const uint32_t b0 = threadIdx.x * DEC_MB, b1 = b0 + DEC_MB;
   TokWin x;
@@ -164,7 +164,8 @@ __device__ __forceinline__ void dec_sweep(const uint8_t *data, uint16_t *ex, uin
     uint32_t code;
     if (kind != TK_OK) code = kind == TK_END ? EX_END : EX_BAD;
     else if (nr < b1) code = ex[skew16((uint32_t)nr)];
-    else code = nr < EX_FAR ? (uint32_t)nr : (EX_FAR | p);
+    else if (nr < EX_FAR) code = (uint32_t)nr;
+    else { code = EX_FAR | p; fin[p] = (uint32_t)((uint64_t)c0 + nr); }   // far jump: its absolute exit goes straight to the SC-exit table
     ex[skew16(p)] = (uint16_t)code;
     // slide the window down by one byte
     if (p > b0)
@@ -175,20 +176,6 @@ __device__ __forceinline__ void dec_sweep(const uint8_t *data, uint16_t *ex, uin
       x.w[0] = (x.w[0] << 8) | nb;
     }
   }
-}
-
-// absolute exit position encoded by a table code (re-parses the far-jumping token)
-template <int W, int BA, int V>
-__device__ __forceinline__ uint32_t dec_code_to_pos(const uint8_t *data, uint32_t code, uint32_t c0, uint32_t clen, bool single)
-{
-  constexpr Spec sp = make_spec(W, BA, V);
-  if (code < EX_FAR) return c0 + code;
-  if (code == EX_END) return POS_END;
-  if (code >= EX_END) return POS_BAD;
-  const uint32_t p = code & 0x3FFFu;
-  SkewReader rd; rd.data = data; rd.p = p;
-  Tok t; dec_parse_rd(sp, single, rd, (uint64_t)clen - (c0 + p), t);
-  return (uint32_t)((uint64_t)c0 + p + t.hdrLen + t.litLen);   // <= clen < POS_SPECIAL for a valid token
 }
 
 // ================================================================================================
@@ -216,7 +203,8 @@ __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   dec_load_sc(S.data, D.in, c0, hs.clen);
   __syncthreads();
-  dec_sweep<W, BA, V>(S.data, S.ex, c0, hs.clen, single);
+  uint32_t *fin = D.finTab + (size_t)c * DEC_SCB;
+  dec_sweep<W, BA, V>(S.data, S.ex, fin, c0, hs.clen, single);
   __syncthreads();
   // keep the mini-block table for D3 (two entries per 4-byte store)
   {
@@ -252,8 +240,21 @@ __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
     __syncthreads();
   }
   // absolute SC exits of every position
-  uint32_t *fin = D.finTab + (size_t)c * DEC_SCB;
-  for (uint32_t p = t; p < DEC_SCB; p += DEC_T) fin[p] = dec_code_to_pos<W, BA, V>(S.data, S.ex[skew16(p)], c0, hs.clen, single);
+  // (the entries of the far-jumping tokens themselves were written by the sweep)
+  for (uint32_t p = t; p < DEC_SCB; p += DEC_T)
+  {
+    const uint32_t code = S.ex[skew16(p)];
+    uint32_t pos;
+    if (code < EX_FAR) pos = c0 + code;
+    else if (code >= EX_END) pos = code == EX_END ? POS_END : POS_BAD;
+    else
+    {
+      const uint32_t q = code & 0x3FFFu;
+      if (q == p) continue;
+      pos = __ldcg(fin + q);
+    }
+    fin[p] = pos;
+  }
 }
 
 // ================================================================================================
@@ -351,7 +352,7 @@ template <int K> struct DecEmitSmem
     } rec;
   } u;
   uint32_t mbEntry[DEC_T];                     // SC-relative entry of the true chain into every mini-block (or 0xFFFF)
-  DecAgg<K> warpAgg[DX_T / 32];
+  DecAgg<K> warpAgg[DX_T / 32 + 1];
   DecAgg<K> bc;
   DecBigOp big[DX_BIGCAP];
   uint32_t nBig, ticket, flag;
@@ -378,12 +379,8 @@ template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_up(const DecAg
   r.sym = __shfl_up_sync(0xFFFFFFFFu, v.sym, d);
   if (K)
   {
-    uint64_t refs = 0;
 #pragma unroll
-    for (int i = 0; i < 7; i++) if (i < K) { r.xf.sym[i] = __shfl_up_sync(0xFFFFFFFFu, v.xf.sym[i], d); refs |= (uint64_t)(uint8_t)v.xf.ref[i] << (8 * i); }
-    refs = __shfl_up_sync(0xFFFFFFFFu, refs, d);
-#pragma unroll
-    for (int i = 0; i < 7; i++) if (i < K) r.xf.ref[i] = (int8_t)(refs >> (8 * i));
+    for (int i = 0; i < 7; i++) if (i < K) r.xf.e[i] = __shfl_up_sync(0xFFFFFFFFu, v.xf.e[i], d);
   }
   return r;
 }
@@ -393,7 +390,7 @@ template <int K> __device__ __forceinline__ void decagg_store(DecAgg<K> *dst, co
   if (K)
   {
 #pragma unroll
-    for (int i = 0; i < 7; i++) if (i < K) { dst->xf.sym[i] = v.xf.sym[i]; dst->xf.ref[i] = v.xf.ref[i]; }
+    for (int i = 0; i < 7; i++) if (i < K) dst->xf.e[i] = v.xf.e[i];
   }
 }
 // L2 loads (the aggregates are written by other CTAs while this kernel runs: never through the non-coherent L1)
@@ -403,14 +400,13 @@ template <int K> __device__ __forceinline__ DecAgg<K> decagg_load_cg(const DecAg
   r.out = __ldcg(&src->out); r.ntok = __ldcg(&src->ntok); r.has = __ldcg(&src->has); r.sym = __ldcg(&src->sym);
   if (K)
   {
-    const unsigned long long refs = __ldcg(reinterpret_cast<const unsigned long long *>(src->xf.ref));
 #pragma unroll
-    for (int i = 0; i < 7; i++) if (i < K) { r.xf.sym[i] = __ldcg(&src->xf.sym[i]); r.xf.ref[i] = (int8_t)(refs >> (8 * i)); }
+    for (int i = 0; i < 7; i++) if (i < K) r.xf.e[i] = __ldcg(&src->xf.e[i]);
   }
   return r;
 }
 
-// exclusive scan over the CTA in thread order; total = combination of everything
+// exclusive scan over the CTA in thread order; total = combination of everything.  warpBuf holds nWarps + 1 entries.
 template <int K> __device__ __forceinline__ DecAgg<K> dec_block_excl_scan(DecAgg<K> *warpBuf, const DecAgg<K> &mine, DecAgg<K> &total)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -426,14 +422,23 @@ template <int K> __device__ __forceinline__ DecAgg<K> dec_block_excl_scan(DecAgg
   DecAgg<K> ex = decagg_shfl_up<K>(inc, 1);
   if (lane == 0) ex = decagg_identity<K>();
   __syncthreads();
-  DecAgg<K> pre = decagg_identity<K>();
-  total = decagg_identity<K>();
-  for (int w = 0; w < nw; w++)
-  {
-    const DecAgg<K> t = warpBuf[w];
-    if (w < warp) pre = decagg_combine<K>(pre, t);
-    total = decagg_combine<K>(total, t);
+  if (warp == 0)
+  { // the warp totals are scanned by one warp: exclusive prefix per warp, grand total in slot nw
+    DecAgg<K> w = decagg_identity<K>();
+    if (lane < nw) w = warpBuf[lane];
+    for (int d = 1; d < nw; d <<= 1)
+    {
+      const DecAgg<K> o = decagg_shfl_up<K>(w, d);
+      if (lane >= d) w = decagg_combine<K>(o, w);
+    }
+    DecAgg<K> wex = decagg_shfl_up<K>(w, 1);
+    if (lane == 0) wex = decagg_identity<K>();
+    if (lane < nw) decagg_store<K>(&warpBuf[lane], wex);
+    if (lane == nw - 1) decagg_store<K>(&warpBuf[nw], w);
   }
+  __syncthreads();
+  const DecAgg<K> pre = warpBuf[warp];
+  total = warpBuf[nw];
   __syncthreads();
   return decagg_combine<K>(pre, ex);
 }
@@ -456,7 +461,7 @@ __device__ __forceinline__ void dec_walk_sizes(const uint8_t *data, uint32_t myE
     if (K)
     {
       const int idx = tk.symKind == 0 ? K : tk.symKind - 2;
-      lutxf_touch(mine.xf, K, idx, tk.symKind == 0 ? rd_sym(rd, tk.symOff, W) : 0);
+      lutxf_touch(mine.xf, K, idx, c0 + p + tk.symOff);
     }
     else if (tk.symKind == 0) { mine.has = 1; mine.sym = rd_sym(rd, tk.symOff, W); }
     if (tk.last) { sawEnd = true; break; }
@@ -492,6 +497,31 @@ __device__ __forceinline__ uint4 dec_lit_vec(const uint8_t *__restrict__ in, uin
   if (sb == 0) return make_uint4(w0, w1, w2, w3);
   const uint32_t w4 = __ldg(sw + 4), sh = sb * 8;
   return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// as dec_lit_vec for a vector of which only bytes [a, b) (0 <= a < b <= 16) are needed: words holding none of them are
+// not read (they may lie before the stream or after its end), `src` may be negative
+__device__ __forceinline__ uint4 dec_lit_vec_part(const uint8_t *__restrict__ in, int64_t src, uint32_t a, uint32_t b)
+{
+  const uint32_t sb = (uint32_t)(src & 3);
+  const int64_t wb = src - sb;                     // aligned stream offset of word 0
+  const int64_t s0 = src + a, s1 = src + b;         // needed stream bytes [s0, s1)
+  uint32_t w[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++)
+  {
+    const int64_t q = wb + 4 * k;
+    w[k] = (q < s1 && q + 4 > s0) ? __ldg(reinterpret_cast<const uint32_t *>(in + q)) : 0u;
+  }
+  const uint32_t sh = sb * 8;
+  return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+}
+// mask of the bytes of word Kw (bytes 4Kw .. 4Kw+3 of a vector) that lie in [a, b)
+template <int Kw> __device__ __forceinline__ uint32_t dec_byte_mask(uint32_t a, uint32_t b)
+{
+  const int lo = max((int)a - 4 * Kw, 0), hi = min((int)b - 4 * Kw, 4);
+  if (hi <= lo) return 0u;
+  const uint32_t mh = hi >= 4 ? 0xFFFFFFFFu : ((1u << (8 * hi)) - 1u);
+  return mh & ~((1u << (8 * lo)) - 1u);
 }
 // 16 bytes of the period-W pattern `sym` starting at pattern offset ph (0 <= ph < W)
 template <int W> __device__ __forceinline__ uint4 dec_run_vec(uint64_t sym, uint32_t ph)
@@ -634,7 +664,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   const Agg before = decagg_combine<K>(exclusive, pre);
   uint64_t symReg = single ? (uint64_t)sc.singleSym : before.sym;     // register starts as zero (src/rleX_extreme_cpu_decode.h:33)
   Lut lut; lut_init(lut, W);
-  if (K) { Lut l0 = lut; lutxf_apply(before.xf, K, l0, lut); }
+  if (K && myEntry != 0xFFFFu) { Lut l0 = lut; lutxf_apply(before.xf, K, W, D.in, l0, lut); }
   uint64_t outPos = before.out;
   const uint64_t scOut1 = exclusive.out + total.out;
   uint64_t *tSym = S.u.rec.tSym;
@@ -674,50 +704,60 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     if (pStart >= pEnd) continue;
 
     // -- phase M: vectors that mix segments (literal / run of neighbouring tokens), one owning token per thread;
-    //    item passN is the partial vector at the start of the pass (its first bytes belong to the pass / SC before)
-    for (uint32_t r = t; r <= passN; r += DX_T)
+    //    item passN is the partial vector at the start of the pass (its first bytes belong to the pass / SC before).
+    //    A vector is assembled segment by segment: 16 bytes of literal source or run pattern, masked to the segment.
     {
-      uint32_t vbs[2]; int nvb = 0; uint32_t r0 = r;
-      if (r == passN) { if (pStart & 15u) vbs[nvb++] = pStart & ~15u; r0 = 0; }
-      else
+      auto mixed = [&](uint32_t vb32, uint32_t r0)
       {
-        const uint32_t o = tOut[r], o1 = tOut[r + 1];
-        const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
-        if (m > o && (m & 15u) && (m & ~15u) >= o) vbs[nvb++] = m & ~15u;
-        if (o1 > m && (o1 & 15u) && (o1 & ~15u) >= m) vbs[nvb++] = o1 & ~15u;
-      }
-      for (int q = 0; q < nvb; q++)
-      {
-        const uint64_t vb = vbs[q];
+        const uint64_t vb = vb32;
         const uint64_t lo = max(vb, (uint64_t)pStart), hi = min(vb + 16, (uint64_t)pEnd);
         uint32_t rr = r0;
         uint64_t tStart = tOut[rr], tNext = tOut[rr + 1];
         uint32_t litLen = tLitLen[rr];
-        uint32_t w4[4] = { 0, 0, 0, 0 };
-#pragma unroll
-        for (int i = 0; i < 16; i++)
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        uint64_t x = lo;
+        while (x < hi)
         {
-          const uint64_t x = vb + i;
-          if (x >= lo && x < hi)
+          while (x >= tNext) { rr++; tStart = tNext; tNext = tOut[rr + 1]; litLen = tLitLen[rr]; }
+          const uint64_t litEnd = min(tStart + litLen, tNext);
+          uint4 cv; uint64_t segEnd;
+          if (x < litEnd)
           {
-            while (x >= tNext) { rr++; tStart = tNext; tNext = tOut[rr + 1]; litLen = tLitLen[rr]; }
-            const uint64_t litEnd = tStart + litLen;
-            uint32_t byte;
-            if (x < litEnd)
-            {
-              const uint32_t sp_ = tLitSrc[rr] + (uint32_t)(x - tStart);
-              byte = (sp_ - c0 < DEC_SCB + DEC_PAD) ? S.data[skew8(sp_ - c0)] : __ldg(in + sp_);
-            }
-            else
-            {
-              const uint32_t ph = (uint32_t)(x - litEnd) % (uint32_t)W;
-              byte = (uint32_t)(tSym[rr] >> (8 * ph)) & 0xFFu;
-            }
-            w4[i >> 2] |= byte << (8 * (i & 3));
+            segEnd = min(litEnd, hi);
+            cv = dec_lit_vec_part(in, (int64_t)tLitSrc[rr] + (int64_t)vb - (int64_t)tStart, (uint32_t)(x - vb), (uint32_t)(segEnd - vb));
+          }
+          else
+          {
+            segEnd = min(tNext, hi);
+            cv = dec_run_vec<W>(tSym[rr], (uint32_t)((vb + 48 - litEnd) % (uint32_t)W));
+          }
+          const uint32_t a = (uint32_t)(x - vb), b = (uint32_t)(segEnd - vb);
+          a0 |= cv.x & dec_byte_mask<0>(a, b); a1 |= cv.y & dec_byte_mask<1>(a, b);
+          a2 |= cv.z & dec_byte_mask<2>(a, b); a3 |= cv.w & dec_byte_mask<3>(a, b);
+          x = segEnd;
+        }
+        if (lo == vb && hi == vb + 16) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(a0, a1, a2, a3);
+        else
+        {
+          const uint32_t ba = (uint32_t)(lo - vb), bb = (uint32_t)(hi - vb);
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+          {
+            const uint32_t wv = (i >> 2) == 0 ? a0 : (i >> 2) == 1 ? a1 : (i >> 2) == 2 ? a2 : a3;
+            if ((uint32_t)i >= ba && (uint32_t)i < bb) out[vb + i] = (uint8_t)(wv >> (8 * (i & 3)));
           }
         }
-        if (lo == vb && hi == vb + 16) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        else for (uint64_t x = lo; x < hi; x++) out[x] = (uint8_t)(w4[(x - vb) >> 2] >> (8 * ((x - vb) & 3)));
+      };
+      for (uint32_t r = t; r <= passN; r += DX_T)
+      {
+        if (r == passN) { if (pStart & 15u) mixed(pStart & ~15u, 0); }
+        else
+        {
+          const uint32_t o = tOut[r], o1 = tOut[r + 1];
+          const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
+          if (m > o && (m & 15u) && (m & ~15u) >= o) mixed(m & ~15u, r);
+          if (o1 > m && (o1 & 15u) && (o1 & ~15u) >= m) mixed(o1 & ~15u, r);
+        }
       }
     }
 
