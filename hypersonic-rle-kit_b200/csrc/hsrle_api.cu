@@ -136,13 +136,14 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   // zero-initialised region first
   D.sc = cv.take<DecScalars>(1);
   D.flagAgg = cv.take<uint32_t>((size_t)D.nSC + 1); D.flagInc = cv.take<uint32_t>((size_t)D.nSC + 1);
+  D.flagSeg = cv.take<uint32_t>((size_t)D.nSeg + 1); D.chainFlag = cv.take<uint32_t>((size_t)D.nSeg + 1);
   if (zeroBytes) *zeroBytes = cv.off;
+  D.chainPos = cv.take<uint32_t>((size_t)D.nSeg + 1);
   D.medList = cv.take<DecBigOp>(((size_t)outSize >> 12) + 16);       // every deferred operation covers more than 4 KiB of output
   D.hugeList = cv.take<DecBigOp>(((size_t)outSize >> 18) + 16);
   D.exTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
   D.finTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
   D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
-  D.segEntry = cv.take<uint32_t>(D.nSeg + 1);
   D.scEntry = cv.take<uint32_t>(D.nSC + 1);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);
   return cv.off + 256;
@@ -272,7 +273,7 @@ static bool dec_prepare(int codec, const DecKernels *k)
   std::lock_guard<std::mutex> lk(g_dattrMu);
   if (!g_composeAttr)
   {
-    if (!cuda_ok(cudaFuncSetAttribute((const void *)k_dec_compose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DEC_SEG * DEC_WIN * 4)), "attr compose")) return false;
+    if (!cuda_ok(cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem)), "attr chain")) return false;
     g_composeAttr = true;
   }
   if (g_dattrDone[codec]) return true;
@@ -296,9 +297,8 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   if (need > wsSize) { g_err = "workspace too small"; return 1; }
   D.in = dIn; D.out = dOut; D.dResult = dResult;
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
-  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DEC_T, k->mapSmem, st, D);
-  HSRLE_LAUNCH(k_dec_compose, D.nSeg, DEC_WIN, DEC_SEG * DEC_WIN * 4, st, D);
-  HSRLE_LAUNCH(k_dec_resolve, 1, D2B_T, 0, st, D);
+  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DM_T, k->mapSmem, st, D);
+  HSRLE_LAUNCH(k_dec_chain, D.nSeg, DC_T, sizeof(DecChainSmem), st, D);
   HSRLE_LAUNCH_NAMED("k_dec_emit", k->emit, D.nSC, DX_T, k->emitSmem, st, D);
   HSRLE_LAUNCH_NAMED("k_dec_big", k->big, num_sms() * 4, 256, 0, st, D);
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;

@@ -50,8 +50,10 @@ constexpr uint32_t POS_NONE = 0xFFFFFFFCu; // no token starts in this SC / segme
 constexpr uint32_t POS_SPECIAL = 0xFFFFFFF0u;
 
 // exit codes of the per-position table (u16, relative to the SC start)
-constexpr uint32_t EX_FAR = 0x8000u;      // | offset of the far-jumping token (exit beyond c0 + 0x7FFF)
-constexpr uint32_t EX_END = 0xC000u, EX_BAD = 0xC001u;
+constexpr uint32_t EX_FAR = 0x8000u;      // first code that is not a position inside [c0, c0 + 0x8000)
+constexpr uint32_t EX_END = 0x8000u, EX_BAD = 0x8001u;
+constexpr uint32_t EX_FARID = 0x8002u;    // + index into the SC's table of far exits
+constexpr uint32_t EX_FARP = 0xC000u;     // | offset of the far-jumping token (table overflow)
 
 struct DecScalars
 {
@@ -59,6 +61,7 @@ struct DecScalars
   uint32_t singleSym;
   uint32_t endSeen;
   uint32_t nTok;
+  uint32_t segTicket;                     // k_dec_chain: dynamic segment ids
   uint32_t ticket, done;                  // k_dec_emit: dynamic SC ids, CTAs finished
   uint32_t emitBad;                       // k_dec_emit met an unparsable token on the true chain
   uint32_t nHuge, nMed;                   // long operations handed to k_dec_big
@@ -183,7 +186,8 @@ struct DecBufs
   uint16_t *exTab;          // [nSC][DEC_SCB]   per-position mini-block exit tables (D1 -> D3)
   uint32_t *finTab;         // [nSC][DEC_SCB]   per-position SC exits, absolute (index = stream position)
   uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
-  uint32_t *segEntry;       // [nSeg] true entry into the segment or POS_NONE
+  uint32_t *flagSeg, *chainFlag;   // [nSeg] "rows published" / "chain position published" (zeroed per call)
+  uint32_t *chainPos;       // [nSeg] first position of the true chain at or after the start of the segment (or its end code)
   uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
   void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals; inclusive prefixes (last SC of every look-back group)
   uint32_t *flagAgg, *flagInc;   // [nSC] "published" flags of the two (zeroed per call)
@@ -196,7 +200,7 @@ struct DecBufs
 HSRLE_HD void dec_header(const Spec &sp, const uint8_t *in, uint32_t inSize, uint32_t outSize, DecScalars &sc)
 {
   sc.status = ST_OK; sc.single = 0; sc.singleSym = 0; sc.endSeen = 0; sc.nTok = 0; sc.n = 0; sc.clen = 0; sc.first = sp.hdr;
-  sc.ticket = 0; sc.done = 0; sc.emitBad = 0; sc.nHuge = 0; sc.nMed = 0; sc.outTotal = 0;
+  sc.segTicket = 0; sc.ticket = 0; sc.done = 0; sc.emitBad = 0; sc.nHuge = 0; sc.nMed = 0; sc.outTotal = 0;
   if (inSize < (uint32_t)sp.hdr) { sc.status = ST_BADARG; return; }
   sc.n = load32(in); sc.clen = load32(in + 4);
   if (sc.n > outSize || sc.clen > inSize || sc.clen < (uint32_t)sp.hdr || sc.clen >= POS_SPECIAL) { sc.status = ST_BADARG; return; }

@@ -136,59 +136,57 @@ __device__ __forceinline__ uint64_t toklen(const TokWin &x, bool single, uint64_
   }
 }
 
-// per-position exit table of the SC: reverse sweep of one mini-block per thread with a sliding window.
-// ex[q] (u16, SC-relative): < EX_FAR: where the chain that starts at q leaves q's mini-block; EX_FAR | q': the
-// token at q' jumps beyond c0 + 0x7FFF; EX_END / EX_BAD.
-template <int W, int BA, int V>
-__device__ __forceinline__ void dec_sweep(const uint8_t *data, uint16_t *ex, uint32_t *fin, uint32_t c0, uint32_t clen, bool single)
+// ================================================================================================
+// D1: per-position exit tables: mini-block level (exTab, for D3) and SC level (finTab, for D2)
+//
+// ex[q] (u16, SC-relative code): < EX_FAR: where the chain that starts at q leaves q's mini-block (after the
+// finalisation: the SC); EX_END / EX_BAD; EX_FARID + id: the chain reaches a token that jumps beyond c0 + 0x7FFF and
+// whose absolute exit is farTab[id]; EX_FARP | q': the same when the SC has more far-jumping tokens than farTab holds
+// (the exit of the token at q' is then parked in its own finTab entry).
+constexpr int DM_T = 256;
+constexpr uint32_t DEC_HB = 64;             // half mini-block: the unit one thread sweeps
+constexpr uint32_t DEC_NFAR = 1536;
+constexpr uint32_t DEC_LIN_BYTES = DEC_SCB + 48;
+__device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
+constexpr uint32_t DEC_EXH_ELEMS = DEC_SCB + (DEC_SCB / 64 + 1) * 2;
+
+struct DecMapSmem
 {
-  const uint32_t b0 = threadIdx.x * DEC_MB, b1 = b0 + DEC_MB;
-  TokWin x;
-  { // window at p = b1 - 1
-    uint32_t p = b1 - 1;
-#pragma unroll
-    for (int k = 0; k < 6; k++)
-    {
-      uint32_t v = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) v |= (uint32_t)data[skew8(p + 4 * k + j)] << (8 * j);
-      x.w[k] = v;
-    }
-  }
-  for (uint32_t p = b1; p-- > b0;)
+  alignas(16) uint8_t data[DEC_LIN_BYTES];     // linear SC image (+ the longest token head after it)
+  alignas(16) uint16_t ex[DEC_EXH_ELEMS];
+  uint32_t farTab[DEC_NFAR];
+  uint32_t nFar;
+};
+constexpr uint32_t DEC_WB = 2048;            // warp-block: the 16 mini-blocks finalised by one warp
+
+// load stream bytes [c0, c0 + DEC_LIN_BYTES) (zero beyond clen), linear -- 16-byte coalesced
+__device__ __forceinline__ void dec_load_sc_linear(uint8_t *data, const uint8_t *__restrict__ in, uint32_t c0, uint32_t clen)
+{
+  constexpr int NV = DEC_LIN_BYTES / 16;
+  const uint4 *src = reinterpret_cast<const uint4 *>(in + c0);
+  const uint32_t avail = clen > c0 ? clen - c0 : 0;
+  for (int v = threadIdx.x; v < NV; v += blockDim.x)
   {
-    const uint32_t pa = c0 + p;
-    uint32_t kind;
-    const uint64_t len = toklen<W, BA, V>(x, single, pa < clen ? (uint64_t)(clen - pa) : 0ull, kind);
-    const uint64_t nr = (uint64_t)p + len;
-    uint32_t code;
-    if (kind != TK_OK) code = kind == TK_END ? EX_END : EX_BAD;
-    else if (nr < b1) code = ex[skew16((uint32_t)nr)];
-    else if (nr < EX_FAR) code = (uint32_t)nr;
-    else { code = EX_FAR | p; fin[p] = (uint32_t)((uint64_t)c0 + nr); }   // far jump: its absolute exit goes straight to the SC-exit table
-    ex[skew16(p)] = (uint16_t)code;
-    // slide the window down by one byte
-    if (p > b0)
-    {
-      const uint32_t nb = data[skew8(p - 1)];
+    const uint32_t b = (uint32_t)v * 16;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (b < avail) x = __ldg(src + v);     // the 16-byte block holding byte clen-1 lies inside the caller's allocation
+    uint32_t w[4] = { x.x, x.y, x.z, x.w };
+    if (b + 16 > avail)
+    { // zero the bytes at and beyond clen so that nothing depends on them
 #pragma unroll
-      for (int k = 5; k > 0; k--) x.w[k] = __funnelshift_l(x.w[k - 1], x.w[k], 8);
-      x.w[0] = (x.w[0] << 8) | nb;
+      for (int k = 0; k < 4; k++)
+      {
+        const uint32_t bb = b + 4 * k;
+        if (bb >= avail) w[k] = 0;
+        else if (bb + 4 > avail) w[k] &= (1u << (8 * (avail - bb))) - 1u;
+      }
     }
+    reinterpret_cast<uint4 *>(data)[v] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
-// ================================================================================================
-// D1: per-position exit tables: mini-block level (exTab, for D3) and SC level (finTab, for D2)
-struct DecMapSmem
-{
-  alignas(16) uint8_t data[DEC_DATA_BYTES];
-  alignas(16) uint16_t ex[DEC_EX_ELEMS];
-};
-constexpr uint32_t DEC_WB = 32 * DEC_MB;    // warp-block: the 32 mini-blocks swept by one warp
-
 template <int W, int BA, int V>
-__global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
+__global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
 {
   constexpr Spec sp = make_spec(W, BA, V);
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -198,55 +196,117 @@ __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
   if (hs.status != ST_OK) return;
   const uint32_t c = blockIdx.x;
   const uint32_t c0 = c * DEC_SCB;
-  if (c0 >= hs.clen) return;
+  const uint32_t clen = hs.clen;
+  if (c0 >= clen) return;
   const bool single = hs.single != 0;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  dec_load_sc(S.data, D.in, c0, hs.clen);
-  __syncthreads();
   uint32_t *fin = D.finTab + (size_t)c * DEC_SCB;
-  dec_sweep<W, BA, V>(S.data, S.ex, fin, c0, hs.clen, single);
+  if (t == 0) S.nFar = 0;
+  dec_load_sc_linear(S.data, D.in, c0, clen);
   __syncthreads();
-  // keep the mini-block table for D3 (two entries per 4-byte store)
+
+  // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
+  //      words give the four 24-byte windows); raw code = where that token ends
   {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(D.exTab + (size_t)c * DEC_SCB);
-    for (uint32_t q = t * 2; q < DEC_SCB; q += DEC_T * 2) dst[q >> 1] = *reinterpret_cast<const uint32_t *>(S.ex + skew16(q));
+    const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.data);
+    for (int it = 0; it < (int)(DEC_SCB / (4 * DM_T)); it++)
+    {
+      const uint32_t p4 = (uint32_t)(it * DM_T + t) * 4;
+      uint32_t w[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) w[k] = d32[(p4 >> 2) + k];
+      uint32_t codes[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+      {
+        TokWin x;
+#pragma unroll
+        for (int k = 0; k < 6; k++) x.w[k] = j ? __funnelshift_r(w[k], w[k + 1], 8 * j) : w[k];
+        const uint32_t p = p4 + j, pa = c0 + p;
+        uint32_t kind;
+        const uint64_t len = toklen<W, BA, V>(x, single, pa < clen ? (uint64_t)(clen - pa) : 0ull, kind);
+        const uint64_t nr = (uint64_t)p + len;
+        uint32_t code;
+        if (kind != TK_OK) code = kind == TK_END ? EX_END : EX_BAD;
+        else if (nr < EX_FAR) code = (uint32_t)nr;
+        else
+        { // far jump: keep its absolute exit
+          const uint32_t id = atomicAdd(&S.nFar, 1u);
+          const uint32_t pos = (uint32_t)((uint64_t)c0 + nr);
+          if (id < DEC_NFAR) { S.farTab[id] = pos; code = EX_FARID + id; }
+          else { fin[p] = pos; code = EX_FARP | p; }
+        }
+        codes[j] = code;
+      }
+      uint32_t *dst = reinterpret_cast<uint32_t *>(S.ex + skew16h(p4));
+      dst[0] = codes[0] | (codes[1] << 16); dst[1] = codes[2] | (codes[3] << 16);
+    }
   }
   __syncthreads();
-  // finalise in place, level 1: inside every warp-block, mini-blocks in reverse order (a code below the end of
-  // the warp-block points into a later mini-block of the same warp-block, which is final already)
+  // ---- phase B: chain exits.  B1: every thread sweeps one half mini-block in reverse (a code below the end of the
+  //      half points to a later entry of the same half, final already)
+  {
+    const uint32_t h0 = (uint32_t)t * DEC_HB, h1 = h0 + DEC_HB;
+    for (uint32_t p = h1; p-- > h0;)
+    {
+      uint32_t code = S.ex[skew16h(p)];
+      if (code < h1) { code = S.ex[skew16h(code)]; S.ex[skew16h(p)] = (uint16_t)code; }
+    }
+  }
+  __syncthreads();
+  //      B2: entries of the lower halves that exit into the upper half of their mini-block take its (final) entry
+  for (uint32_t i = t; i < DEC_SCB / 2; i += DM_T)
+  {
+    const uint32_t mb = i / DEC_HB, p = mb * DEC_MB + (i % DEC_HB);
+    const uint32_t code = S.ex[skew16h(p)];
+    if (code < (mb + 1) * DEC_MB) S.ex[skew16h(p)] = S.ex[skew16h(code)];
+  }
+  __syncthreads();
+  // keep the mini-block table for D3 (eight entries per 16-byte store)
+  {
+    uint4 *dst = reinterpret_cast<uint4 *>(D.exTab + (size_t)c * DEC_SCB);
+    for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
+    {
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(S.ex + skew16h(q));
+      dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
+    }
+  }
+  __syncthreads();
+  // finalise in place, level 1: inside every warp-block, mini-blocks in reverse order (a code below the end of the
+  // warp-block points into a later mini-block of the same warp-block, which is final already)
   {
     const uint32_t wb0 = warp * DEC_WB, wb1 = wb0 + DEC_WB;
-    for (int mb = 30; mb >= 0; mb--)
+    for (int mb = (int)(DEC_WB / DEC_MB) - 2; mb >= 0; mb--)
     {
       uint32_t code[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) code[k] = S.ex[skew16(wb0 + mb * DEC_MB + lane + 32 * k)];
+      for (int k = 0; k < 4; k++) code[k] = S.ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)];
 #pragma unroll
-      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = S.ex[skew16(code[k])];
+      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = S.ex[skew16h(code[k])];
 #pragma unroll
-      for (int k = 0; k < 4; k++) S.ex[skew16(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
+      for (int k = 0; k < 4; k++) S.ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
       __syncwarp();
     }
   }
   __syncthreads();
   // level 2: warp-blocks in reverse order
-  for (int wb = DEC_T / 32 - 2; wb >= 0; wb--)
+  for (int wb = (int)(DEC_SCB / DEC_WB) - 2; wb >= 0; wb--)
   {
-    for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DEC_T)
+    for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DM_T)
     {
-      uint32_t code = S.ex[skew16(p)];
-      if (code < DEC_SCB) { code = S.ex[skew16(code)]; S.ex[skew16(p)] = (uint16_t)code; }
+      uint32_t code = S.ex[skew16h(p)];
+      if (code < DEC_SCB) { code = S.ex[skew16h(code)]; S.ex[skew16h(p)] = (uint16_t)code; }
     }
     __syncthreads();
   }
-  // absolute SC exits of every position
-  // (the entries of the far-jumping tokens themselves were written by the sweep)
-  for (uint32_t p = t; p < DEC_SCB; p += DEC_T)
+  // absolute SC exits of every position (overflowed far-jumping tokens wrote their own entries in phase A)
+  for (uint32_t p = t; p < DEC_SCB; p += DM_T)
   {
-    const uint32_t code = S.ex[skew16(p)];
+    const uint32_t code = S.ex[skew16h(p)];
     uint32_t pos;
     if (code < EX_FAR) pos = c0 + code;
-    else if (code >= EX_END) pos = code == EX_END ? POS_END : POS_BAD;
+    else if (code < EX_FARID) pos = code == EX_END ? POS_END : POS_BAD;
+    else if (code < EX_FARP) pos = S.farTab[code - EX_FARID];
     else
     {
       const uint32_t q = code & 0x3FFFu;
@@ -258,73 +318,109 @@ __global__ void __launch_bounds__(DEC_T) k_dec_map(const DecBufs D)
 }
 
 // ================================================================================================
-// D2a: per segment, where does the chain that enters SC c at window offset w leave the segment
-static __global__ void __launch_bounds__(DEC_WIN) k_dec_compose(const DecBufs D)
+// D2: k_dec_chain -- one CTA per segment of DEC_SEG SCs, one thread per window offset:
+//   (1) the windowed SC-exit rows of the segment are fetched into shared memory in one round trip;
+//   (2) composed in reverse SC order: suf[i][w] = where the chain that enters SC i at window offset w leaves the
+//       SEGMENT (entries beyond the window -- after a long literal -- cost one finTab look-up per SC instead);
+//   (3) the segment's rows are published; (4) thread 0 follows the true chain from the stream start (or from the
+//       nearest chain position a preceding segment has published) through the published rows up to its own segment;
+//   (5) and walks its SCs forward through the raw rows, recording every SC's true entry.
+constexpr int DC_T = (int)DEC_WIN;
+struct DecChainSmem
+{
+  uint32_t raw[DEC_SEG][DEC_WIN];
+  uint32_t suf[DEC_SEG][DEC_WIN];
+  uint32_t ticket, entry;
+};
+constexpr int DC_LOOKBACK = 8;
+
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v);
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p);
+
+static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  uint32_t *suf = reinterpret_cast<uint32_t *>(smemRaw);   // [DEC_SEG][DEC_WIN]
-  const DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;
-  const uint32_t nSC = (sc.clen + DEC_SCB - 1) / DEC_SCB;
-  const uint32_t g = blockIdx.x;
+  DecChainSmem &S = *reinterpret_cast<DecChainSmem *>(smemRaw);
+  DecScalars &sc = *D.sc;
+  if (sc.status != ST_OK) return;                 // header check of D1: uniform over the grid
+  const uint32_t w = threadIdx.x;
+  if (w == 0) S.ticket = atomicAdd(&sc.segTicket, 1u);
+  __syncthreads();
+  const uint32_t g = S.ticket;
+  const uint32_t clen = sc.clen;
+  const uint32_t nSC = (clen + DEC_SCB - 1) / DEC_SCB;
+  const uint32_t nSegEff = (nSC + DEC_SEG - 1) / DEC_SEG;
   const uint32_t cFirst = g * DEC_SEG;
+  for (uint32_t c = cFirst + w; c < min(cFirst + DEC_SEG, D.nSC); c += DC_T) D.scEntry[c] = POS_NONE;
   if (cFirst >= nSC) return;
   const uint32_t nHere = min(DEC_SEG, nSC - cFirst);
   const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_SCB;
+  const uint64_t segBytes = (uint64_t)DEC_SEG * DEC_SCB;
   const uint32_t *__restrict__ fin = D.finTab;
-  const uint32_t w = threadIdx.x;
+  // (1)
+#pragma unroll 8
+  for (uint32_t i = 0; i < nHere; i++) S.raw[i][w] = __ldg(fin + (size_t)(cFirst + i) * DEC_SCB + w);
+  __syncthreads();
+  // (2)
   for (int i = (int)nHere - 1; i >= 0; i--)
   {
-    uint32_t x = fin[(size_t)(cFirst + i) * DEC_SCB + w];
+    uint32_t x = S.raw[i][w];
     while (x < POS_SPECIAL && (uint64_t)x < segEnd)
     {
       const uint32_t c2 = x / DEC_SCB, off = x - c2 * DEC_SCB;
-      if (off < DEC_WIN) { x = suf[(c2 - cFirst) * DEC_WIN + off]; break; }   // a later SC of the segment: final already
-      x = fin[x];                                                             // entry beyond the window: one SC at a time
+      if (off < DEC_WIN) { x = S.suf[c2 - cFirst][off]; break; }    // a later SC of the segment: final already
+      x = __ldg(fin + x);                                           // entry beyond the window: one SC at a time
     }
-    suf[i * DEC_WIN + w] = x;
+    S.suf[i][w] = x;
     __syncthreads();
   }
-  uint32_t *dst = D.sufExit + (size_t)cFirst * DEC_WIN;
-  for (uint32_t i = 0; i < nHere; i++) dst[i * DEC_WIN + w] = suf[i * DEC_WIN + w];
-}
-
-// ================================================================================================
-// D2b: chain the segments, record the true entry of every SC
-constexpr int D2B_T = 1024;
-
-static __global__ void __launch_bounds__(D2B_T) k_dec_resolve(const DecBufs D)
-{
-  DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;
-  const uint32_t clen = sc.clen;
-  const uint32_t nSC = (clen + DEC_SCB - 1) / DEC_SCB;
-  const uint32_t nSeg = (nSC + DEC_SEG - 1) / DEC_SEG;
-  const uint32_t *__restrict__ fin = D.finTab;
-  for (uint32_t c = threadIdx.x; c < D.nSC; c += blockDim.x) D.scEntry[c] = POS_NONE;
-  for (uint32_t g = threadIdx.x; g < nSeg; g += blockDim.x) D.segEntry[g] = POS_NONE;
-  __syncthreads();
-  if (threadIdx.x == 0)
+  // (3)
   {
-    uint32_t pos = sc.first, lastSeg = 0xFFFFFFFFu;
-    while (pos < POS_SPECIAL)
-    {
-      if (pos >= clen) { pos = POS_BAD; break; }
-      const uint32_t c = pos / DEC_SCB, g = c / DEC_SEG, off = pos - c * DEC_SCB;
-      if (g != lastSeg) { D.segEntry[g] = pos; lastSeg = g; }
-      pos = off < DEC_WIN ? D.sufExit[(size_t)c * DEC_WIN + off] : fin[pos];
-    }
-    if (pos != POS_END) sc.status = ST_BADSTREAM;
+    uint32_t *dst = D.sufExit + (size_t)cFirst * DEC_WIN;
+    for (uint32_t i = 0; i < nHere; i++) dst[i * DEC_WIN + w] = S.suf[i][w];
   }
+  __threadfence();
   __syncthreads();
-  for (uint32_t g = threadIdx.x; g < nSeg; g += blockDim.x)
+  if (w == 0)
   {
-    uint32_t pos = D.segEntry[g];
-    const uint64_t segEnd = (uint64_t)(g + 1) * DEC_SEG * DEC_SCB;
-    while (pos < POS_SPECIAL && (uint64_t)pos < segEnd && pos < clen)
+    st_volatile_u32(D.flagSeg + g, 1u);
+    // (4)
+    uint32_t pos = sc.first;
+    for (int k = (int)g - 1; k >= 0 && k >= (int)g - DC_LOOKBACK; k--)
+      if (ld_volatile_u32(D.chainFlag + k)) { __threadfence(); pos = __ldcg(D.chainPos + k); break; }
+    while (pos < POS_SPECIAL && pos < clen && (uint64_t)pos / segBytes < g)
     {
-      D.scEntry[pos / DEC_SCB] = pos;
-      pos = fin[pos];
+      const uint32_t c = pos / DEC_SCB, off = pos - c * DEC_SCB;
+      if (off < DEC_WIN)
+      {
+        const uint32_t k = c / DEC_SEG;
+        while (ld_volatile_u32(D.flagSeg + k) == 0u) { }
+        __threadfence();
+        pos = __ldcg(D.sufExit + (size_t)c * DEC_WIN + off);
+      }
+      else pos = __ldg(fin + pos);
+    }
+    // pos: the first position of the true chain at or after the start of this segment (or how the chain ended)
+    D.chainPos[g] = pos; __threadfence(); st_volatile_u32(D.chainFlag + g, 1u);
+    S.entry = (pos < POS_SPECIAL && pos < clen && (uint64_t)pos < segEnd) ? pos : POS_NONE;
+    if (g == nSegEff - 1)
+    { // the last segment settles whether the chain reaches the terminator
+      uint32_t x = pos;
+      while (x < POS_SPECIAL)
+      {
+        if (x >= clen) { x = POS_BAD; break; }
+        const uint32_t c = x / DEC_SCB, off = x - c * DEC_SCB;
+        x = off < DEC_WIN ? S.suf[c - cFirst][off] : __ldg(fin + x);
+      }
+      if (x != POS_END) sc.status = ST_BADSTREAM;
+    }
+    // (5)
+    uint32_t p = S.entry;
+    while (p < POS_SPECIAL && (uint64_t)p < segEnd && p < clen)
+    {
+      const uint32_t c = p / DEC_SCB, off = p - c * DEC_SCB;
+      D.scEntry[c] = p;
+      p = off < DEC_WIN ? S.raw[c - cFirst][off] : __ldg(fin + p);
     }
   }
 }
