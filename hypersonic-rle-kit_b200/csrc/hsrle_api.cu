@@ -102,7 +102,8 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   if (zeroBytes) *zeroBytes = cv.off;
   B.runA = cv.take<uint32_t>(B.maxRuns); B.runB = cv.take<uint32_t>(B.maxRuns);
   B.runSym = cv.take<uint64_t>(sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns);
-  B.cIn = cv.take<AutoState>(maxChunks); B.cLut = cv.take<Lut>(sp.K ? maxChunks : 1);
+  B.cIn = cv.take<AutoState>(maxChunks); B.cLut = cv.take<Lut>(sp.K ? maxChunks : 1); B.cKnown = cv.take<uint8_t>(sp.K ? maxChunks : 1);
+  B.scFo = cv.take<Lut>(sp.K ? B.maxSC : 1); B.scFlags = cv.take<uint8_t>(sp.K ? B.maxSC : 1);
   B.scIn = cv.take<AutoState>(B.maxSC); B.scLut = cv.take<Lut>(sp.K ? B.maxSC : 1);
   B.scSum = cv.take<ChunkSum>(B.maxSC); B.scAgg = cv.take<LutAgg>(sp.K ? B.maxSC : 1);
   B.scBytes = cv.take<uint64_t>(B.maxSC); B.scTok = cv.take<uint32_t>(B.maxSC); B.scBase = cv.take<uint64_t>(B.maxSC);

@@ -258,7 +258,9 @@ HSRLE_HD LutAgg lutagg_combine(const LutAgg &older, const LutAgg &newer, int K)
 // Encoder: evaluate one match-mask run [a,b) (M[p]==1 for a<=p<b, maximal, b-a >= sp.minM).
 // Returns EV_* flags.  With EV_EMIT, [s,e) is the run, `h` its header bytes (everything before the
 // literal), and the literal is in[lastBefore, s).  State is advanced either way.
-enum : uint32_t { EV_VALID = 1, EV_EMIT = 2, EV_SYMSET = 4 };
+enum : uint32_t { EV_VALID = 1, EV_EMIT = 2, EV_SYMSET = 4, EV_STATE_MASK = 7,
+                  EV_MARG = 8,           // LUT codecs: the decision would flip between "symbol in the table" and "not in the table"
+                  EV_IDX_SHIFT = 8 };    // LUT codecs: table index of the symbol (K = absent) in bits 8..10
 // `sym0` = the W input bytes in[a-W, a) (the first period of the run the mask run [a,b) belongs to).
 template <class Sink>
 HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a, uint32_t b, AutoState &st, Lut &lut, LutAgg *agg,
@@ -285,8 +287,10 @@ HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a
     const uint32_t rng = s - st.last + 2;
     const int idx = lut_find(lut, K, sym);
     const uint32_t stored = (W == 1 || sp.byteAlign) ? cnt - 1 : cnt / W - 3 / W + 2;
-    const uint32_t pen = (rng <= 0xFFFFFu ? (rng <= TR ? 0u : 2u) : 4u) + (stored <= 0xFFFFFu ? (stored <= TC ? 0u : 2u) : 4u) + (idx == K ? 1u : 0u);
-    if (!(cnt >= (uint32_t)sp.LONG || cnt >= 3 + pen)) return EV_VALID;
+    const uint32_t penBase = (rng <= 0xFFFFFu ? (rng <= TR ? 0u : 2u) : 4u) + (stored <= 0xFFFFFu ? (stored <= TC ? 0u : 2u) : 4u);
+    const uint32_t pen = penBase + (idx == K ? 1u : 0u);
+    const uint32_t info = ((uint32_t)idx << EV_IDX_SHIFT) | ((cnt < (uint32_t)sp.LONG && cnt == 3 + penBase) ? (uint32_t)EV_MARG : 0u);
+    if (!(cnt >= (uint32_t)sp.LONG || cnt >= 3 + pen)) return EV_VALID | info;
     lut_touch(lut, K, idx, sym);
     if (agg) lutagg_push(*agg, K, sym);
     const uint32_t c7 = stored <= TC ? stored : (stored <= 0xFFFFu ? 1u : 0u);
@@ -296,7 +300,7 @@ HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a
     if (stored != c7) { if (stored <= 0xFFFFu) h.put16(stored); else h.put32(stored); }
     if (rng != r7) { if (rng <= 0xFFFFu) h.put16(rng); else h.put32(rng); }
     st.last = e;
-    return EV_VALID | EV_EMIT;
+    return EV_VALID | EV_EMIT | info;
   }
 
   const uint32_t rng = s - st.last + 1;

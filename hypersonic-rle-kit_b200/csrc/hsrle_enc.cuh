@@ -34,6 +34,9 @@ constexpr int E2_T = 128;                 // threads per super-chunk CTA
 constexpr int E2_CH = 4;                  // records per thread
 constexpr int E2_WARM = 12;               // records a thread warms its state guess up on
 constexpr int E2_SCR = E2_T * E2_CH;      // records per super-chunk
+constexpr int E2L_CH = 16;                // LUT codecs: records per lane -- one warp owns a whole super-chunk
+static_assert(E2L_CH * 32 == E2_SCR && E2L_CH % E2_CH == 0, "a warp covers one super-chunk");
+constexpr uint32_t SCF_SENS = 1;          // scFlags: a decision of the super-chunk depended on the incoming LUT
 constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
 constexpr int E2_ROUNDS = 5;              // grid-level rounds (the last one ends with the sequential repair)
 constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
@@ -101,10 +104,12 @@ struct EncBufs
   uint32_t maxRuns, maxSC;
   unsigned long long *tileStatus;        // E1 look-back: [2t] aggregate, [2t+1] inclusive prefix: flag(1) | ends(31) | starts(31)
   uint32_t *runA, *runB; void *runSym;   // records: mask run [a,b), first-period symbol (u32 if W <= 4 else u64)
-  AutoState *cIn; Lut *cLut;             // per 16-record chunk: exact incoming state (written by E2, read by E3)
+  AutoState *cIn; Lut *cLut;             // per 4-record chunk: incoming state (written by E2, read by E3); for LUT codecs the
+  uint8_t *cKnown;                       //   first cKnown entries of cLut are exact, the rest follow from scLut (enc_chunk_lut)
   AutoState *scIn; Lut *scLut;           // per super-chunk: assumed incoming state
   ChunkSum *scSum; LutAgg *scAgg;        // per super-chunk: summary under the current decisions
-  uint64_t *scBytes; uint32_t *scTok;    // per super-chunk: token bytes / tokens
+  uint64_t *scBytes; uint32_t *scTok;    // per super-chunk: token bytes (LUT codecs: without the symbol bytes of scFo) / tokens
+  Lut *scFo; uint8_t *scFlags;           // LUT codecs: symbols in order of first emission (scAgg.m of them), SCF_* flags
   uint64_t *scBase;                      // per super-chunk: exclusive token-byte offset
   uint8_t *scDirty;
   CopyDesc *bigList, *medList;
@@ -194,6 +199,40 @@ template <int K> HSRLE_HD void segsum_apply(AutoState &st, Lut &lut, const SegSu
 {
   chunksum_apply(st, s.cs);
   if (K) lut_apply(lut, K, s.agg);
+}
+
+// LUT codecs.  While fewer than K distinct symbols have been emitted inside a super-chunk, the table is
+// (those symbols, most recent first) followed by what is left of the super-chunk's incoming table.  A super-chunk
+// evaluated from a GUESSED incoming table is still exact -- decisions, state summary, aggregate -- unless one of its
+// decisions was marginal (EV_MARG) for a symbol outside the known front part: only such "sensitive" super-chunks
+// have to be re-run when the guess turns out wrong.  What does change with the incoming table is whether the first
+// emission of each of the <= K symbols of scFo found its symbol in the table (no symbol bytes) or not (W bytes).
+HSRLE_HD uint32_t enc_fo_misses(const Lut &fo, uint32_t m, int K, const Lut &incoming)
+{
+  Lut l = incoming;
+  uint32_t misses = 0;
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
+  {
+    if (i < K && i < (int)m)
+    {
+      const int idx = lut_find(l, K, fo.s[i]);
+      if (idx == K) misses++;
+      lut_touch(l, K, idx, fo.s[i]);
+    }
+  }
+  return misses;
+}
+// exact incoming table of a chunk: its `known` leading entries, then the super-chunk's exact incoming table
+HSRLE_HD void enc_chunk_lut(Lut &chunkLut, uint32_t known, int K, const Lut &scIncoming)
+{
+  if ((int)known >= K) return;
+  LutAgg a; a.m = known;
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++) a.s[i] = chunkLut.s[i];
+  Lut l = scIncoming;
+  lut_apply(l, K, a);
+  chunkLut = l;
 }
 
 // state guess for a chunk whose predecessor records are unknown: "a run was just emitted right before

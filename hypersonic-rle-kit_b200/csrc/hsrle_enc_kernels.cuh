@@ -1,6 +1,7 @@
 // hsrle_enc_kernels.cuh -- sm_100a kernels of the encoder (see hsrle_enc.cuh for the pipeline).
 #pragma once
 #include <cuda_runtime.h>
+#include <type_traits>
 #include "hsrle_enc.cuh"
 #include "hsrle_slice.cuh"
 
@@ -243,33 +244,60 @@ template <int W, int BA, int V, class SymT> struct EncCta
   using Seg = SegSum<K>;
   static constexpr int NREC = E2_SCR + E2_WARM;               // with the warm-up halo
   static constexpr int NSLOT = NREC + NREC / E2_CH + 1;
+  // LUT codecs: one warp per super-chunk, E2L_CH records per lane (the scan element carries the LUT aggregate, so a
+  // 32-element warp scan instead of a 128-element block scan is what makes them affordable)
+  static constexpr int NW = E2_T / 32;
+  static constexpr int NSLOTL = NREC + NREC / E2L_CH + 2;
 
-  struct Smem
+  struct CtaRecs
   {
     uint32_t a[NSLOT], b[NSLOT];
     SymT sym[NSLOT];
+    AutoState serSt[E2_T];                                      // states produced by the in-CTA sequential pass
+  };
+  struct WarpRecs
+  {
+    uint32_t a[NSLOTL], b[NSLOTL];
+    SymT sym[NSLOTL];
+    AutoState serSt[32]; Lut serLut[32];
+    uint64_t fo[8];
+    uint32_t foMiss, sens;
+  };
+  struct Smem
+  {
+    typename std::conditional<K != 0, WarpRecs[NW], CtaRecs>::type r;
     Seg warpTot[E2_T / 32];
+    Seg bcTot;
     AutoState bcSt; Lut bcLut;                                  // broadcast slots
-    AutoState serSt[E2_T]; Lut serLut[K ? E2_T : 1];            // states produced by the in-CTA sequential pass
+    uint64_t warpBytes[E2_T / 32];
     uint32_t flag;
   };
 
-  // evaluate records [j0,j1) (local indices) from (st,lut); returns the segment summary
-  template <bool COUNT_ONLY>
-  static __device__ __forceinline__ Seg eval_range(const Smem &S, uint32_t n, uint32_t floor, int j0, int j1, AutoState &st, Lut &lut)
+  // evaluate records [j0,j1) (local indices; record j lives in slot j + j / CHS) from (st,lut); returns the segment summary
+  // sens0 (LUT codecs): set when a decision was marginal for a symbol that had not been emitted earlier in [j0,j1) --
+  // only then can the range's decisions depend on the table it started from (hsrle_enc.cuh)
+  template <int CHS>
+  static __device__ __forceinline__ Seg eval_range(const uint32_t *ra, const uint32_t *rb, const SymT *rs, uint32_t n, uint32_t floor, int j0, int j1,
+                                                   AutoState &st, Lut &lut, uint32_t *sens0 = nullptr)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     Seg r = segsum_identity<K>();
-    uint32_t fl = 0;
+    uint32_t fl = 0, known = 0, sens = 0;
     for (int j = j0; j < j1; j++)
     {
-      const int q = rec_slot(j);
+      const int q = j + j / CHS;
       uint32_t s, e; CountSink h;
       const uint32_t lastBefore = st.last;
-      const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &r.agg : nullptr, s, e, h);
-      fl |= ev;
+      const uint32_t ev = enc_eval(sp, (uint64_t)rs[q], n, ra[q], rb[q], st, lut, K ? &r.agg : nullptr, s, e, h);
+      fl |= ev & EV_STATE_MASK;
       if (ev & EV_EMIT) { r.bytes += h.len + slice_lit_len(lastBefore, s, floor); r.ntok++; }
+      if constexpr (K != 0)
+      {
+        const uint32_t idx = (ev >> EV_IDX_SHIFT) & 7u;
+        if ((ev & EV_VALID) && idx >= known && known < (uint32_t)K) { if (ev & EV_MARG) sens = 1; if (ev & EV_EMIT) known++; }
+      }
     }
+    if (K && sens0) *sens0 = sens;
     r.cs.flags = fl; r.cs.last = st.last; r.cs.cursor = st.cursor; r.cs.lastSym = st.lastSym;
     return r;
   }
@@ -312,7 +340,8 @@ template <int W, int BA, int V, class SymT> struct EncCta
   // One super-chunk.  given == true: (gSt,gLut) is the incoming state to use for the first chunk;
   // otherwise it is guessed by warming up over the halo chunk.  Writes the per-chunk incoming states,
   // the super-chunk summary and (when guessed) the assumed incoming state.
-  static __device__ void process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
+  template <int KK = K>
+  static __device__ typename std::enable_if<KK == 0>::type process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     const uint32_t nRuns = B.sc->nRuns, n = B.n, floor = B.sliceLo, endShift = B.sc->endShift;
@@ -325,7 +354,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     {
       const uint32_t g = lo + j - E2_WARM;
       const int q = rec_slot(j);
-      S.a[q] = B.runA[g]; S.b[q] = B.runB[g + endShift]; S.sym[q] = runSym[g];
+      S.r.a[q] = B.runA[g]; S.r.b[q] = B.runB[g + endShift]; S.r.sym[q] = runSym[g];
     }
     __syncthreads();
     const int t = threadIdx.x;
@@ -339,11 +368,11 @@ template <int W, int BA, int V, class SymT> struct EncCta
     else
     { // warm up over the preceding E2_WARM records from the neutral guess
       const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
-      enc_neutral_state(sp, (active && w0 < j0) ? S.a[rec_slot(w0)] : 0u, stIn, lutIn);
-      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<true>(S, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+      enc_neutral_state(sp, (active && w0 < j0) ? S.r.a[rec_slot(w0)] : 0u, stIn, lutIn);
+      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
     }
     Seg mine = segsum_identity<K>();
-    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut); }
+    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut); }
 
     // fixed point of (scan -> compare -> re-run)
     AutoState st0; Lut lut0;   // incoming state of the super-chunk = what thread 0 used
@@ -361,7 +390,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       if (active && t > 0 && state_differs(want, wantLut, stIn, lutIn))
       {
         stIn = want; lutIn = wantLut; changed = 1;
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut);
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut);
       }
       if (!__syncthreads_or(changed)) { converged = true; break; }
     }
@@ -372,17 +401,17 @@ template <int W, int BA, int V, class SymT> struct EncCta
         AutoState st = st0; Lut lut = lut0;
         for (int c = 0; c * E2_CH < (int)cnt; c++)
         {
-          S.serSt[c] = st; if (K) S.serLut[K ? c : 0] = lut;
+          S.r.serSt[c] = st;
           const int a0 = E2_WARM + c * E2_CH, a1 = min(a0 + E2_CH, E2_WARM + (int)cnt);
-          (void)eval_range<true>(S, n, floor, a0, a1, st, lut);
+          (void)eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, a0, a1, st, lut);
         }
         atomicAdd(&B.sc->innerSerial, 1u);
       }
       __syncthreads();
       if (active)
       {
-        stIn = S.serSt[t]; if (K) lutIn = S.serLut[K ? t : 0];
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<true>(S, n, floor, j0, j1, st, lut);
+        stIn = S.r.serSt[t];
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut);
       }
       (void)block_excl_scan(S, mine, total);
     }
@@ -398,6 +427,157 @@ template <int W, int BA, int V, class SymT> struct EncCta
       B.scSum[s] = total.cs; if (K) B.scAgg[s] = total.agg;
       B.scBytes[s] = total.bytes; B.scTok[s] = total.ntok;
       if (!given) { B.scIn[s] = st0; if (K) B.scLut[s] = lut0; }
+    }
+    totalOut = total;
+  }
+
+
+  // ---- LUT codecs: one super-chunk per WARP.  Same contract as the CTA variant; additionally publishes what the
+  //      sensitivity scheme needs (hsrle_enc.cuh: enc_fo_misses / enc_chunk_lut): scFo, scFlags, cKnown, and scBytes
+  //      without the symbol bytes of the first emissions.
+  static __device__ __forceinline__ void warp_scan(const Seg &mine, Seg &pre, Seg &total)
+  {
+    const int lane = threadIdx.x & 31;
+    Seg inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const Seg o = shfl_up_t(inc, d);
+      if (lane >= d) inc = segsum_combine<K>(o, inc);
+    }
+    pre = shfl_up_t(inc, 1);
+    if (lane == 0) pre = segsum_identity<K>();
+    total = shfl_idx_t(inc, 31);
+  }
+
+  template <int KK = K>
+  static __device__ typename std::enable_if<KK != 0>::type process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
+  {
+    constexpr Spec sp = make_spec(W, BA, V);
+    const int lane = threadIdx.x & 31;
+    WarpRecs &R = S.r[threadIdx.x >> 5];
+    const uint32_t nRuns = B.sc->nRuns, n = B.n, floor = B.sliceLo, endShift = B.sc->endShift;
+    const uint32_t lo = s * E2_SCR;
+    const uint32_t cnt = min((uint32_t)E2_SCR, nRuns - lo);
+    const int halo = (s > 0) ? E2_WARM : 0;
+    const SymT *runSym = reinterpret_cast<const SymT *>(B.runSym);
+    __syncwarp();
+    for (int j = lane + (E2_WARM - halo); j < E2_WARM + (int)cnt; j += 32)
+    {
+      const uint32_t g = lo + j - E2_WARM;
+      const int q = j + j / E2L_CH;
+      R.a[q] = B.runA[g]; R.b[q] = B.runB[g + endShift]; R.sym[q] = runSym[g];
+    }
+    if (lane == 0) { R.foMiss = 0; R.sens = 0; }
+    __syncwarp();
+    const int j0 = E2_WARM + lane * E2L_CH;
+    const int j1 = min(j0 + E2L_CH, E2_WARM + (int)cnt);
+    const bool active = j0 < j1;
+
+    AutoState stIn; Lut lutIn;
+    if (lane == 0 && given) { stIn = gSt; lutIn = gLut; }
+    else if (lane == 0 && s == 0) enc_stream_incoming(B, W, stIn, lutIn);
+    else
+    { // warm up over the preceding E2_WARM records from the neutral guess
+      const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
+      enc_neutral_state(sp, (active && w0 < j0) ? R.a[w0 + w0 / E2L_CH] : 0u, stIn, lutIn);
+      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+    }
+    Seg mine = segsum_identity<K>();
+    uint32_t sens0 = 0;
+    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0); }
+    const AutoState st0 = shfl_idx_t(stIn, 0);
+    const Lut lut0 = shfl_idx_t(lutIn, 0);
+
+    // fixed point of (scan -> compare -> re-run).  A lane whose decisions cannot depend on the table it started from
+    // (sens0 == 0) only takes the exact table; its summary stands (its byte count is redone by the final pass).
+    Seg pre, total;
+    bool converged = false;
+    for (int it = 0; it < E2_MAXIT; it++)
+    {
+      warp_scan(mine, pre, total);
+      AutoState want = st0; Lut wantLut = lut0;
+      segsum_apply<K>(want, wantLut, pre);
+      int changed = 0;
+      if (active && lane > 0)
+      {
+        const bool lutDiff = !lut_equal(wantLut, lutIn, K);
+        if (want != stIn || (lutDiff && sens0))
+        {
+          stIn = want; lutIn = wantLut; changed = 1;
+          AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0);
+        }
+        else if (lutDiff) lutIn = wantLut;
+      }
+      if (!__any_sync(0xFFFFFFFFu, changed)) { converged = true; break; }
+    }
+    if (!converged)
+    { // exact sequential pass: lane 0 threads the state through every lane's records
+      if (lane == 0)
+      {
+        AutoState st = st0; Lut lut = lut0;
+        for (int c = 0; c * E2L_CH < (int)cnt; c++)
+        {
+          R.serSt[c] = st; R.serLut[c] = lut;
+          const int a0 = E2_WARM + c * E2L_CH, a1 = min(a0 + E2L_CH, E2_WARM + (int)cnt);
+          (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, a0, a1, st, lut);
+        }
+        atomicAdd(&B.sc->innerSerial, 1u);
+      }
+      __syncwarp();
+      if (active)
+      {
+        stIn = R.serSt[lane]; lutIn = R.serLut[lane];
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut);
+      }
+      warp_scan(mine, pre, total);
+    }
+    // final pass: per-chunk incoming states for E3, sensitivity, first emissions
+    if (active)
+    {
+      AutoState st = stIn; Lut lut = lutIn;
+      uint32_t known = pre.agg.m, sensL = 0;
+      uint64_t bytesL = 0;
+      for (int j = j0; j < j1; j++)
+      {
+        if (((j - j0) & (E2_CH - 1)) == 0)
+        {
+          const uint32_t chunk = s * E2_T + (uint32_t)(j - E2_WARM) / E2_CH;
+          B.cIn[chunk] = st; B.cLut[chunk] = lut; B.cKnown[chunk] = (uint8_t)known;
+        }
+        const int q = j + j / E2L_CH;
+        uint32_t rs, re; CountSink h;
+        const uint32_t lastBefore = st.last;
+        const uint32_t ev = enc_eval(sp, (uint64_t)R.sym[q], n, R.a[q], R.b[q], st, lut, nullptr, rs, re, h);
+        if (ev & EV_EMIT) bytesL += h.len + slice_lit_len(lastBefore, rs, floor);
+        const uint32_t idx = (ev >> EV_IDX_SHIFT) & 7u;
+        if ((ev & EV_VALID) && known < (uint32_t)K && idx >= known)
+        {
+          if (ev & EV_MARG) sensL = 1;
+          if (ev & EV_EMIT) { R.fo[known] = lut.s[0]; if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
+        }
+      }
+      if (sensL) R.sens = 1;
+      mine.bytes = bytesL;
+    }
+    else mine.bytes = 0;
+    { // exact (under the incoming table this run used) token bytes of the super-chunk
+      uint64_t b = mine.bytes;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) b += __shfl_xor_sync(0xFFFFFFFFu, b, d);
+      total.bytes = b;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+      B.scSum[s] = total.cs; B.scAgg[s] = total.agg;
+      B.scBytes[s] = total.bytes - (uint64_t)W * R.foMiss; B.scTok[s] = total.ntok;
+      Lut fo;
+#pragma unroll
+      for (int i = 0; i < 7; i++) fo.s[i] = (i < K && i < (int)total.agg.m) ? R.fo[i] : 0ull;
+      B.scFo[s] = fo; B.scFlags[s] = R.sens ? (uint8_t)SCF_SENS : (uint8_t)0;
+      if (!given) { B.scIn[s] = st0; B.scLut[s] = lut0; }
+      __threadfence();                                            // read by the round's last CTA
     }
     totalOut = total;
   }
@@ -451,51 +631,71 @@ template <int W, int BA, int V, class SymT> struct EncCta
     if (fOk) { const uint32_t src = fin.last; for (uint32_t k = threadIdx.x; k < fLen; k += blockDim.x) B.out[fPos + k] = B.in[src + k]; }
   }
 
+  // exact token bytes of super-chunk s when its incoming table is `lut`
+  static __device__ __forceinline__ uint64_t sc_bytes(const EncBufs &B, uint32_t s, const Lut &lut)
+  {
+    uint64_t b = B.scBytes[s];
+    if (K) { const uint32_t m = B.scAgg[s].m; if (m) b += (uint64_t)W * enc_fo_misses(B.scFo[s], m, K, lut); }
+    return b;
+  }
+
   static __device__ void scan_verify(const EncBufs &B, Smem &S, int round)
   {
     EncScalars &sc = *B.sc;
     const uint32_t nSC = sc.nSC;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     __shared__ uint32_t sDirty, sFirst;
     if (t == 0) { sDirty = 0; sFirst = 0xFFFFFFFFu; }
     const uint32_t per = (nSC + E2_T - 1) / E2_T;
     const uint32_t lo = min(nSC, (uint32_t)t * per), hi = min(nSC, lo + per);
+    // (1) states: scan of the summaries (token bytes follow in (3): for LUT codecs they depend on the incoming table)
     Seg mine = segsum_identity<K>();
     for (uint32_t s = lo; s < hi; s++)
     {
-      Seg e; e.cs = B.scSum[s]; if (K) e.agg = B.scAgg[s]; else e.agg.m = 0; e.bytes = B.scBytes[s]; e.ntok = B.scTok[s];
+      Seg e; e.cs = B.scSum[s]; if (K) e.agg = B.scAgg[s]; else e.agg.m = 0; e.bytes = 0; e.ntok = B.scTok[s];
       mine = segsum_combine<K>(mine, e);
     }
     Seg total;
     const Seg pre = block_excl_scan(S, mine, total);
+    // (2) verification; a LUT super-chunk whose decisions did not depend on the incoming table only takes the exact table
     AutoState st; Lut lut; enc_stream_incoming(B, W, st, lut);
     segsum_apply<K>(st, lut, pre);
-    uint64_t bytes = pre.bytes;
+    uint64_t bytes = 0;
     uint32_t nd = 0, first = 0xFFFFFFFFu;
     for (uint32_t s = lo; s < hi; s++)
     {
       bool bad = false;
       if (B.scIn[s] != st) { B.scIn[s] = st; bad = true; }
-      if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; bad = true; }
+      if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; if (B.scFlags[s] & SCF_SENS) bad = true; }
       B.scDirty[s] = bad ? 1 : 0;
       if (bad) { if (!nd) first = s; nd++; }
-      B.scBase[s] = bytes;
+      B.scBase[s] = bytes;                       // relative to the thread's first super-chunk until (3)
+      bytes += sc_bytes(B, s, lut);
       chunksum_apply(st, B.scSum[s]);
       if (K) lut_apply(lut, K, B.scAgg[s]);
-      bytes += B.scBytes[s];
     }
     if (nd) { atomicAdd(&sDirty, nd); atomicMin(&sFirst, first); }
+    // (3) token byte offsets: scan of the per-thread sums
+    uint64_t incB = bytes;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, incB, d); if (lane >= d) incB += o; }
+    if (lane == 31) S.warpBytes[warp] = incB;
     __syncthreads();
+    uint64_t preB = incB - bytes, totalBytes = 0;
+#pragma unroll
+    for (int w = 0; w < E2_T / 32; w++) { const uint64_t x = S.warpBytes[w]; if (w < warp) preB += x; totalBytes += x; }
+    for (uint32_t s = lo; s < hi; s++) B.scBase[s] += preB;
     const uint32_t nDirty = sDirty, firstDirty = sFirst;
     if (t == 0) { sc.nDirty[round] = nDirty; sc.firstDirty[round] = firstDirty; }
     __syncthreads();
     AutoState fin; Lut finLut; enc_stream_incoming(B, W, fin, finLut);
     segsum_apply<K>(fin, finLut, total);
-    if (nDirty == 0) { finish(B, fin, finLut, total.bytes, total.ntok); return; }
+    if (nDirty == 0) { finish(B, fin, finLut, totalBytes, total.ntok); return; }
     if (round < E2_ROUNDS - 1) return;
 
     // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
-    // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA, parallel inside)
+    // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA / one warp each)
+    __threadfence();
     if (t == 0) { S.bcSt = B.scIn[firstDirty]; if (K) S.bcLut = B.scLut[firstDirty]; }
     __syncthreads();
     AutoState run = S.bcSt; Lut runLut; if (K) runLut = S.bcLut; else lut_init(runLut, W);
@@ -506,13 +706,25 @@ template <int W, int BA, int V, class SymT> struct EncCta
     {
       Seg tot;
       bool need = B.scDirty[s] != 0 || B.scIn[s] != run;               // uniform: every thread reads the same words
-      if (K && !need) need = !lut_equal(B.scLut[s], runLut, K);
+      const bool lutDiff = K && !lut_equal(B.scLut[s], runLut, K);
+      if (lutDiff && (B.scFlags[s] & SCF_SENS)) need = true;
+      __syncthreads();
       if (need)
       {
-        process(B, S, s, true, run, runLut, tot);
+        if (K)
+        {
+          if (warp == 0) { process(B, S, s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
+          __syncthreads();
+          tot = S.bcTot;
+        }
+        else process(B, S, s, true, run, runLut, tot);
         if (t == 0) { B.scIn[s] = run; if (K) B.scLut[s] = runLut; B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
       }
-      else { tot.cs = B.scSum[s]; if (K) tot.agg = B.scAgg[s]; else tot.agg.m = 0; tot.bytes = B.scBytes[s]; tot.ntok = B.scTok[s]; }
+      else
+      {
+        tot.cs = B.scSum[s]; if (K) tot.agg = B.scAgg[s]; else tot.agg.m = 0; tot.bytes = sc_bytes(B, s, runLut); tot.ntok = B.scTok[s];
+        if (t == 0 && lutDiff) B.scLut[s] = runLut;
+      }
       if (t == 0) B.scBase[s] = runBytes;
       segsum_apply<K>(run, runLut, tot);
       runBytes += tot.bytes; runTok += tot.ntok;
@@ -531,7 +743,9 @@ __global__ void __launch_bounds__(E2_T) k_enc_auto(const EncBufs B, int round)
   EncScalars &sc = *B.sc;
   if (round > 0 && sc.nDirty[round - 1] == 0) return;
   const uint32_t nSC = sc.nSC;
-  for (uint32_t s = blockIdx.x; s < nSC; s += gridDim.x)
+  constexpr int SCS_PER_CTA = C::K ? C::NW : 1;                        // LUT codecs: one super-chunk per warp
+  const uint32_t sFirst = C::K ? blockIdx.x * SCS_PER_CTA + (threadIdx.x >> 5) : blockIdx.x;
+  for (uint32_t s = sFirst; s < nSC; s += gridDim.x * SCS_PER_CTA)
   {
     typename C::Seg tot;
     if (round == 0) { AutoState d = enc_initial_state(); Lut dl; lut_init(dl, W); C::process(B, S, s, false, d, dl, tot); }
@@ -639,7 +853,11 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     const int j0 = E2_CH + t * E2_CH, j1 = min(j0 + E2_CH, E2_CH + (int)cnt);
     const bool active = j0 < j1;
     AutoState st0 = enc_initial_state(); Lut lut0; lut_init(lut0, W);
-    if (active) { st0 = B.cIn[s * E2_T + t]; if (K) lut0 = B.cLut[s * E2_T + t]; }
+    if (active)
+    {
+      st0 = B.cIn[s * E2_T + t];
+      if (K) { lut0 = B.cLut[s * E2_T + t]; enc_chunk_lut(lut0, B.cKnown[s * E2_T + t], K, B.scLut[s]); }
+    }
     // pass 1: bytes of my chunk
     unsigned long long mine = 0;
     if (active)

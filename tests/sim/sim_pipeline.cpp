@@ -61,7 +61,7 @@ struct SimEnc
       uint32_t s, e; TokenHdr h;
       const uint32_t lastBefore = st.last;
       const uint32_t ev = enc_eval(sp, runSym[j], n, runA[j], runB[j], st, lut, K ? &r.agg : nullptr, s, e, h);
-      fl |= ev;
+      fl |= ev & EV_STATE_MASK;
       if (ev & EV_EMIT)
       {
         const uint32_t lit = s - lastBefore;
