@@ -422,7 +422,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--quick", action="store_true", help="skip the CPU baseline and the per-codec detail (sweeps)")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent codec calls of a step are dealt to")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent codec calls of a step are dealt to")
     ap.add_argument("--threads", type=int, default=4, help="host threads calling the host-pointer entry points in the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -143,7 +143,9 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.medList = cv.take<DecBigOp>(((size_t)outSize >> 12) + 16);       // every deferred operation covers more than 4 KiB of output
   D.hugeList = cv.take<DecBigOp>(((size_t)outSize >> 18) + 16);
   D.exTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
-  D.finTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
+  D.scTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
+  D.farTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
+  D.winTab = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
   D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
   D.scEntry = cv.take<uint32_t>(D.nSC + 1);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);

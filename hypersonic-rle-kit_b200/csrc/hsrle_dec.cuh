@@ -52,8 +52,7 @@ constexpr uint32_t POS_SPECIAL = 0xFFFFFFF0u;
 // exit codes of the per-position table (u16, relative to the SC start)
 constexpr uint32_t EX_FAR = 0x8000u;      // first code that is not a position inside [c0, c0 + 0x8000)
 constexpr uint32_t EX_END = 0x8000u, EX_BAD = 0x8001u;
-constexpr uint32_t EX_FARID = 0x8002u;    // + index into the SC's table of far exits
-constexpr uint32_t EX_FARP = 0xC000u;     // | offset of the far-jumping token (table overflow)
+constexpr uint32_t EX_FARP = 0xC000u;     // | offset of the far-jumping token (its absolute exit: farTab)
 
 struct DecScalars
 {
@@ -184,7 +183,9 @@ struct DecBufs
   uint8_t *out; uint32_t outSize;
   uint32_t nSC, nSeg;
   uint16_t *exTab;          // [nSC][DEC_SCB]   per-position mini-block exit tables (D1 -> D3)
-  uint32_t *finTab;         // [nSC][DEC_SCB]   per-position SC exits, absolute (index = stream position)
+  uint16_t *scTab;          // [nSC][DEC_SCB]   per-position SC exit codes (D1 -> D2)
+  uint32_t *farTab;         // [nSC][DEC_SCB]   absolute exit of the far-jumping token at that position (sparse)
+  uint32_t *winTab;         // [nSC][DEC_WIN]   absolute SC exits of the window positions
   uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
   uint32_t *flagSeg, *chainFlag;   // [nSeg] "rows published" / "chain position published" (zeroed per call)
   uint32_t *chainPos;       // [nSeg] first position of the true chain at or after the start of the segment (or its end code)

@@ -60,7 +60,7 @@ template <int K> __device__ __forceinline__ uint32_t win_u32(const TokWin &x)
 enum : uint32_t { TK_OK = 0, TK_END = 1, TK_BAD = 2 };
 
 // [S symbol bytes][cnt][rng] with 8-bit fields and 0-escapes (plain tokens; S = 0 for single-symbol streams)
-template <int S> __device__ __forceinline__ uint64_t toklen_plain(const TokWin &x, uint64_t avail, uint32_t &kind)
+template <int S> __device__ __forceinline__ uint32_t toklen_plain(const TokWin &x, uint32_t avail, uint32_t &kind)
 {
   const uint32_t c = win_u8<S>(x);
   const bool e1 = c == 0;
@@ -70,12 +70,12 @@ template <int S> __device__ __forceinline__ uint64_t toklen_plain(const TokWin &
   const bool e2 = r == 0;
   const uint32_t hdr = S + 2 + (e1 ? 4u : 0u) + (e2 ? 4u : 0u);
   const uint32_t rng = e2 ? r32 : r;
-  const uint64_t len = (uint64_t)hdr + rng - 1;
-  kind = (hdr > avail) ? TK_BAD : (rng == 0) ? TK_END : (len > avail) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
-  return len;
+  // (a token fits iff hdr <= avail and rng - 1 <= avail - hdr: no 64-bit arithmetic; len is only used when it fits)
+  kind = (hdr > avail) ? TK_BAD : (rng == 0) ? TK_END : (rng - 1 > avail - hdr) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
+  return hdr + rng - 1;
 }
 // packed tokens: b0 = same<<7 | cnt7, optional u32 cnt, optional symbol, rng in the 7-bit or the 8-bit style
-template <int W, bool RNG7> __device__ __forceinline__ uint64_t toklen_packed(const TokWin &x, uint64_t avail, uint32_t &kind)
+template <int W, bool RNG7> __device__ __forceinline__ uint32_t toklen_packed(const TokWin &x, uint32_t avail, uint32_t &kind)
 {
   const uint32_t b0 = win_u8<0>(x);
   const bool e1 = (b0 & 0x7F) == 0, same = (b0 & 0x80) != 0;
@@ -99,12 +99,11 @@ template <int W, bool RNG7> __device__ __forceinline__ uint64_t toklen_packed(co
     hdr = o + (esc ? 5u : 1u);
     endMark = esc && rng == 0;
   }
-  const uint64_t len = (uint64_t)hdr + rng - 1;
-  kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng == 0 || len > avail) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
-  return len;
+  kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng == 0 || rng - 1 > avail - hdr) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
+  return hdr + rng - 1;
 }
 // LUT tokens: u16 head = idx | cnt7 | rng, optional symbol, optional u16/u32 cnt, optional u16/u32 rng
-template <int W, int K> __device__ __forceinline__ uint64_t toklen_lut(const TokWin &x, uint64_t avail, uint32_t &kind)
+template <int W, int K> __device__ __forceinline__ uint32_t toklen_lut(const TokWin &x, uint32_t avail, uint32_t &kind)
 {
   constexpr int RB = (K == 3) ? 7 : 6;
   const uint32_t head = win_u32<0>(x) & 0xFFFFu;
@@ -119,12 +118,11 @@ template <int W, int K> __device__ __forceinline__ uint64_t toklen_lut(const Tok
   const uint32_t rng = r == 1 ? (x2 & 0xFFFFu) : (r == 0 ? x2 : r);
   const uint32_t hdr = 2 + (miss ? (uint32_t)W : 0u) + ce + re;
   const bool endMark = r == 1 && rng == 0;
-  const uint64_t len = (uint64_t)hdr + rng - 2;
-  kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng < 2 || len > avail) ? TK_BAD : (cnt == 0) ? TK_END : TK_OK;
-  return len;
+  kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng < 2 || rng - 2 > avail - hdr) ? TK_BAD : (cnt == 0) ? TK_END : TK_OK;
+  return hdr + rng - 2;
 }
 template <int W, int BA, int V>
-__device__ __forceinline__ uint64_t toklen(const TokWin &x, bool single, uint64_t avail, uint32_t &kind)
+__device__ __forceinline__ uint32_t toklen(const TokWin &x, bool single, uint32_t avail, uint32_t &kind)
 {
   constexpr Spec sp = make_spec(W, BA, V);
   if constexpr (sp.K != 0) return toklen_lut<W, sp.K>(x, avail, kind);
@@ -137,15 +135,15 @@ __device__ __forceinline__ uint64_t toklen(const TokWin &x, bool single, uint64_
 }
 
 // ================================================================================================
-// D1: per-position exit tables: mini-block level (exTab, for D3) and SC level (finTab, for D2)
+// D1: per-position exit tables, one CTA per SC.
 //
-// ex[q] (u16, SC-relative code): < EX_FAR: where the chain that starts at q leaves q's mini-block (after the
-// finalisation: the SC); EX_END / EX_BAD; EX_FARID + id: the chain reaches a token that jumps beyond c0 + 0x7FFF and
-// whose absolute exit is farTab[id]; EX_FARP | q': the same when the SC has more far-jumping tokens than farTab holds
-// (the exit of the token at q' is then parked in its own finTab entry).
+// ex[q] (u16, SC-relative code): < EX_FAR: where the chain that starts at q leaves q's mini-block (exTab, kept for D3) /
+// the SC (scTab, after the two-level in-place finalisation), a position of [c0, c0 + 0x8000); EX_END / EX_BAD;
+// EX_FARP | q': the chain reaches the token at q', which jumps beyond c0 + 0x7FFF and whose absolute exit is
+// farTab[c0 + q'].  D2 reads the table as codes and translates the few entries it needs; only the first DEC_WIN entries
+// of an SC (its windowed exit map, read by every call of D2) are also kept as absolute positions (winTab).
 constexpr int DM_T = 256;
 constexpr uint32_t DEC_HB = 64;             // half mini-block: the unit one thread sweeps
-constexpr uint32_t DEC_NFAR = 1536;
 constexpr uint32_t DEC_LIN_BYTES = DEC_SCB + 48;
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
 constexpr uint32_t DEC_EXH_ELEMS = DEC_SCB + (DEC_SCB / 64 + 1) * 2;
@@ -154,8 +152,6 @@ struct DecMapSmem
 {
   alignas(16) uint8_t data[DEC_LIN_BYTES];     // linear SC image (+ the longest token head after it)
   alignas(16) uint16_t ex[DEC_EXH_ELEMS];
-  uint32_t farTab[DEC_NFAR];
-  uint32_t nFar;
 };
 constexpr uint32_t DEC_WB = 2048;            // warp-block: the 16 mini-blocks finalised by one warp
 
@@ -185,6 +181,20 @@ __device__ __forceinline__ void dec_load_sc_linear(uint8_t *data, const uint8_t 
   }
 }
 
+// absolute position (or POS_END / POS_BAD) a final exit code of SC c stands for
+__device__ __forceinline__ uint32_t dec_code_pos(uint32_t code, uint32_t c0, const uint32_t *farRow)
+{
+  if (code < EX_FAR) return c0 + code;
+  if (code < EX_FARP) return code == EX_END ? POS_END : POS_BAD;
+  return __ldcg(farRow + (code & 0x3FFFu));
+}
+// where the chain that starts at stream position x (< clen) leaves x's SC
+__device__ __forceinline__ uint32_t dec_sc_exit(const DecBufs &D, uint32_t x)
+{
+  const uint32_t c0 = (x / DEC_SCB) * DEC_SCB;
+  return dec_code_pos(__ldg(D.scTab + x), c0, D.farTab + (size_t)c0);
+}
+
 template <int W, int BA, int V>
 __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
 {
@@ -200,8 +210,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   if (c0 >= clen) return;
   const bool single = hs.single != 0;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  uint32_t *fin = D.finTab + (size_t)c * DEC_SCB;
-  if (t == 0) S.nFar = 0;
+  uint32_t *farRow = D.farTab + (size_t)c0;
   dec_load_sc_linear(S.data, D.in, c0, clen);
   __syncthreads();
 
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   //      words give the four 24-byte windows); raw code = where that token ends
   {
     const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.data);
+    const uint32_t availSC = clen - c0;              // stream bytes from the start of the SC
     for (int it = 0; it < (int)(DEC_SCB / (4 * DM_T)); it++)
     {
       const uint32_t p4 = (uint32_t)(it * DM_T + t) * 4;
@@ -222,19 +232,15 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
         TokWin x;
 #pragma unroll
         for (int k = 0; k < 6; k++) x.w[k] = j ? __funnelshift_r(w[k], w[k + 1], 8 * j) : w[k];
-        const uint32_t p = p4 + j, pa = c0 + p;
+        const uint32_t p = p4 + j;
         uint32_t kind;
-        const uint64_t len = toklen<W, BA, V>(x, single, pa < clen ? (uint64_t)(clen - pa) : 0ull, kind);
-        const uint64_t nr = (uint64_t)p + len;
-        uint32_t code;
-        if (kind != TK_OK) code = kind == TK_END ? EX_END : EX_BAD;
-        else if (nr < EX_FAR) code = (uint32_t)nr;
-        else
-        { // far jump: keep its absolute exit
-          const uint32_t id = atomicAdd(&S.nFar, 1u);
-          const uint32_t pos = (uint32_t)((uint64_t)c0 + nr);
-          if (id < DEC_NFAR) { S.farTab[id] = pos; code = EX_FARID + id; }
-          else { fin[p] = pos; code = EX_FARP | p; }
+        const uint32_t len = toklen<W, BA, V>(x, single, p < availSC ? availSC - p : 0u, kind);
+        const uint32_t nr = p + len;                  // <= availSC when the token fits
+        uint32_t code = kind == TK_END ? EX_END : EX_BAD;
+        if (kind == TK_OK)
+        {
+          code = nr;
+          if (nr >= EX_FAR) { farRow[p] = c0 + nr; code = EX_FARP | p; }   // far jump: its absolute exit is parked in its own farTab entry
         }
         codes[j] = code;
       }
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     }
   }
   __syncthreads();
-  // finalise in place, level 1: inside every warp-block, mini-blocks in reverse order (a code below the end of the
+  // warp-block level, in place: inside every warp-block, mini-blocks in reverse order (a code below the end of the
   // warp-block points into a later mini-block of the same warp-block, which is final already)
   {
     const uint32_t wb0 = warp * DEC_WB, wb1 = wb0 + DEC_WB;
@@ -289,7 +295,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     }
   }
   __syncthreads();
-  // level 2: warp-blocks in reverse order
+  // SC level: warp-blocks in reverse order
   for (int wb = (int)(DEC_SCB / DEC_WB) - 2; wb >= 0; wb--)
   {
     for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DM_T)
@@ -299,22 +305,17 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     }
     __syncthreads();
   }
-  // absolute SC exits of every position (overflowed far-jumping tokens wrote their own entries in phase A)
-  for (uint32_t p = t; p < DEC_SCB; p += DM_T)
+  // keep the SC table for D2 (as codes: D2 translates the few entries it reads)
   {
-    const uint32_t code = S.ex[skew16h(p)];
-    uint32_t pos;
-    if (code < EX_FAR) pos = c0 + code;
-    else if (code < EX_FARID) pos = code == EX_END ? POS_END : POS_BAD;
-    else if (code < EX_FARP) pos = S.farTab[code - EX_FARID];
-    else
+    uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
+    for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
     {
-      const uint32_t q = code & 0x3FFFu;
-      if (q == p) continue;
-      pos = __ldcg(fin + q);
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(S.ex + skew16h(q));
+      dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
     }
-    fin[p] = pos;
   }
+  // absolute SC exits of the window positions
+  for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = dec_code_pos(S.ex[skew16h(w)], c0, farRow);
 }
 
 // ================================================================================================
@@ -356,10 +357,9 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
   const uint32_t nHere = min(DEC_SEG, nSC - cFirst);
   const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_SCB;
   const uint64_t segBytes = (uint64_t)DEC_SEG * DEC_SCB;
-  const uint32_t *__restrict__ fin = D.finTab;
   // (1)
 #pragma unroll 8
-  for (uint32_t i = 0; i < nHere; i++) S.raw[i][w] = __ldg(fin + (size_t)(cFirst + i) * DEC_SCB + w);
+  for (uint32_t i = 0; i < nHere; i++) S.raw[i][w] = __ldg(D.winTab + (size_t)(cFirst + i) * DEC_WIN + w);
   __syncthreads();
   // (2)
   for (int i = (int)nHere - 1; i >= 0; i--)
@@ -369,7 +369,7 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
     {
       const uint32_t c2 = x / DEC_SCB, off = x - c2 * DEC_SCB;
       if (off < DEC_WIN) { x = S.suf[c2 - cFirst][off]; break; }    // a later SC of the segment: final already
-      x = __ldg(fin + x);                                           // entry beyond the window: one SC at a time
+      x = dec_sc_exit(D, x);                                        // entry beyond the window: one SC at a time
     }
     S.suf[i][w] = x;
     __syncthreads();
@@ -398,7 +398,7 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
         __threadfence();
         pos = __ldcg(D.sufExit + (size_t)c * DEC_WIN + off);
       }
-      else pos = __ldg(fin + pos);
+      else pos = dec_sc_exit(D, pos);
     }
     // pos: the first position of the true chain at or after the start of this segment (or how the chain ended)
     D.chainPos[g] = pos; __threadfence(); st_volatile_u32(D.chainFlag + g, 1u);
@@ -410,7 +410,7 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
       {
         if (x >= clen) { x = POS_BAD; break; }
         const uint32_t c = x / DEC_SCB, off = x - c * DEC_SCB;
-        x = off < DEC_WIN ? S.suf[c - cFirst][off] : __ldg(fin + x);
+        x = off < DEC_WIN ? S.suf[c - cFirst][off] : dec_sc_exit(D, x);
       }
       if (x != POS_END) sc.status = ST_BADSTREAM;
     }
@@ -420,7 +420,7 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
     {
       const uint32_t c = p / DEC_SCB, off = p - c * DEC_SCB;
       D.scEntry[c] = p;
-      p = off < DEC_WIN ? S.raw[c - cFirst][off] : __ldg(fin + p);
+      p = off < DEC_WIN ? S.raw[c - cFirst][off] : dec_sc_exit(D, p);
     }
   }
 }

@@ -38,7 +38,7 @@ constexpr int E2L_CH = 16;                // LUT codecs: records per lane -- one
 static_assert(E2L_CH * 32 == E2_SCR && E2L_CH % E2_CH == 0, "a warp covers one super-chunk");
 constexpr uint32_t SCF_SENS = 1;          // scFlags: a decision of the super-chunk depended on the incoming LUT
 constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
-constexpr int E2_ROUNDS = 5;              // grid-level rounds (the last one ends with the sequential repair)
+constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
 constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
 constexpr uint32_t BIG_COPY = 65536;      // ... and these are split over the whole grid
 

@@ -93,7 +93,7 @@ int main(int argc, char **argv)
       chunksum_apply(st, o.cs); if (sp.K) lut_apply(lut, sp.K, o.agg);
     }
   }
-  for (int scheme = 0; scheme < 2; scheme++)
+  for (int scheme = 0; scheme < 3; scheme++)
   {
     std::vector<AutoState> usedIn(nSC); std::vector<Lut> usedLut(nSC); std::vector<ScOut> out(nSC);
     // round 0: neutral guess warmed up over WARM records
@@ -124,7 +124,14 @@ int main(int argc, char **argv)
         bool bad = usedIn[s] != st;
         const bool lutDiff = sp.K && !lut_equal(usedLut[s], lut, sp.K);
         if (scheme == 0) bad = bad || lutDiff;
-        else bad = bad || (lutDiff && out[s].sens);
+        else if (scheme == 1) bad = bad || (lutDiff && out[s].sens);
+        else if (!bad && lutDiff && out[s].sens)
+        { // ideal criterion: would a re-run change the summary?
+          ScOut o2 = run_sc(s * SCR, std::min(recs.size(), (s + 1) * SCR), st, lut);
+          bad = o2.cs.last != out[s].cs.last || o2.cs.flags != out[s].cs.flags || o2.ntok != out[s].ntok || o2.agg.m != out[s].agg.m;
+          for (int i = 0; i < sp.K && i < (int)o2.agg.m; i++) bad = bad || o2.agg.s[i] != out[s].agg.s[i];
+          if (!bad) usedLut[s] = lut;
+        }
         nSens += out[s].sens;
         if (bad) { dirty[s] = 1; nDirty++; usedIn[s] = st; usedLut[s] = lut; }
         chunksum_apply(st, out[s].cs); if (sp.K) lut_apply(lut, sp.K, out[s].agg);
