@@ -86,13 +86,33 @@ static const EncKernels *enc_kernels_for(int codec)
   return k->scan ? k : nullptr;
 }
 
+// E1 tile size: one CTA per tile, about 4 CTAs resident per SM.  A grid that is a little larger than a whole number of
+// waves leaves the last wave almost empty (88 MB in 128-KiB tiles: 675 tiles on 592 slots), so pick the steps per warp
+// (multiple of 4) that minimises waves x tile time, with a fixed per-tile cost (ticket, look-back, two barriers) of
+// about two steps.  Depends only on the vector count and the SM count: deterministic per call, as the workspace layout
+// needs it.
+static uint32_t enc_scan_steps(uint32_t nVec)
+{
+  const uint64_t slots = (uint64_t)num_sms() * 4;
+  uint32_t best = E1_STEPS; uint64_t bestCost = ~0ull;
+  for (uint32_t steps = 8; steps <= (uint32_t)E1_STEPS; steps += 4)
+  {
+    const uint64_t tiles = ((uint64_t)nVec + (uint64_t)E1_T * steps - 1) / ((uint64_t)E1_T * steps);
+    const uint64_t waves = (tiles + slots - 1) / slots;
+    const uint64_t cost = waves * (steps + 2);
+    if (cost < bestCost || (cost == bestCost && steps > best)) { best = steps; bestCost = cost; }
+  }
+  return best;
+}
+
 static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t *zeroBytes)
 {
   Carver cv{ (uint8_t *)ws, 0 };
   B.n = n;
   B.nVec = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
   B.lastVec = (n - 1) >> 4;
-  B.nTiles = (B.nVec + E1_TILE_VECS - 1) / E1_TILE_VECS;
+  B.scanSteps = enc_scan_steps(B.nVec);
+  B.nTiles = (B.nVec + E1_T * B.scanSteps - 1) / (E1_T * B.scanSteps);
   B.maxRuns = n / (sp.minM + 1) + 2;
   B.maxSC = B.maxRuns / E2_SCR + 2;
   const size_t maxChunks = (size_t)B.maxSC * E2_T;
@@ -138,6 +158,7 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.sc = cv.take<DecScalars>(1);
   D.flagAgg = cv.take<uint32_t>((size_t)D.nSC + 1); D.flagInc = cv.take<uint32_t>((size_t)D.nSC + 1);
   D.flagSeg = cv.take<uint32_t>((size_t)D.nSeg + 1); D.chainFlag = cv.take<uint32_t>((size_t)D.nSeg + 1);
+  D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);          // zeroed: 0 = "row not published yet"
   if (zeroBytes) *zeroBytes = cv.off;
   D.chainPos = cv.take<uint32_t>((size_t)D.nSeg + 1);
   D.medList = cv.take<DecBigOp>(((size_t)outSize >> 12) + 16);       // every deferred operation covers more than 4 KiB of output
@@ -146,7 +167,6 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.scTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
   D.farTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
   D.winTab = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
-  D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
   D.scEntry = cv.take<uint32_t>(D.nSC + 1);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);
   return cv.off + 256;
@@ -212,7 +232,8 @@ static size_t slice_carve(EncBufs &B, const Spec &sp, uint32_t n, uint32_t lo, u
   const uint32_t nVecGlobal = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
   const uint32_t vecs = last ? nVecGlobal - B.vecBase : len / 16;
   B.nVec = vecs;
-  B.nTiles = (vecs + E1_TILE_VECS - 1) / E1_TILE_VECS;
+  B.scanSteps = enc_scan_steps(vecs);
+  B.nTiles = (vecs + E1_T * B.scanSteps - 1) / (E1_T * B.scanSteps);
   B.lastVec = last ? (n - 1) >> 4 : hi / 16;        // non-last ranks may load the first vector of the tail halo
   B.maxRuns += 2;
   B.outBase = SLICE_PORCH;

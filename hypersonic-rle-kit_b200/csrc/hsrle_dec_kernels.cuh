@@ -360,11 +360,52 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
   // (1)
 #pragma unroll 8
   for (uint32_t i = 0; i < nHere; i++) S.raw[i][w] = __ldg(D.winTab + (size_t)(cFirst + i) * DEC_WIN + w);
+  // (1b) chains that enter a later SC of the segment beyond its window need a table look-up in global memory per
+  //      SC.  The first hops of all rows are independent of each other: take them now, many loads in flight, instead
+  //      of one dependent round trip per row inside the sequential composition below.
+  constexpr int DC_PREHOPS = 2, DC_BATCH = 16;
+#pragma unroll 1
+  for (int hop = 0; hop < DC_PREHOPS; hop++)
+  {
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < nHere; i0 += DC_BATCH)
+    {
+      uint32_t x[DC_BATCH], code[DC_BATCH], farv[DC_BATCH]; bool need[DC_BATCH];
+#pragma unroll
+      for (int k = 0; k < DC_BATCH; k++)
+      {
+        const uint32_t i = i0 + k;
+        x[k] = i < nHere ? (hop == 0 ? S.raw[i][w] : S.suf[i][w]) : POS_NONE;
+        need[k] = x[k] < POS_SPECIAL && (uint64_t)x[k] < segEnd && (x[k] % DEC_SCB) >= DEC_WIN;
+      }
+#pragma unroll
+      for (int k = 0; k < DC_BATCH; k++) code[k] = __ldg(D.scTab + (need[k] ? x[k] : 0u));          // unconditional: all in flight together
+#pragma unroll
+      for (int k = 0; k < DC_BATCH; k++)
+      {
+        const bool far = need[k] && code[k] >= EX_FARP;
+        farv[k] = __ldcg(D.farTab + (far ? (size_t)(x[k] / DEC_SCB) * DEC_SCB + (code[k] & 0x3FFFu) : (size_t)0));
+      }
+#pragma unroll
+      for (int k = 0; k < DC_BATCH; k++)
+      {
+        const uint32_t i = i0 + k;
+        if (i >= nHere) continue;
+        uint32_t y = x[k];
+        if (need[k])
+        {
+          const uint32_t c0 = (x[k] / DEC_SCB) * DEC_SCB;
+          y = code[k] < EX_FAR ? c0 + code[k] : code[k] < EX_FARP ? (code[k] == EX_END ? POS_END : POS_BAD) : farv[k];
+        }
+        S.suf[i][w] = y;
+      }
+    }
+  }
   __syncthreads();
   // (2)
   for (int i = (int)nHere - 1; i >= 0; i--)
   {
-    uint32_t x = S.raw[i][w];
+    uint32_t x = S.suf[i][w];
     while (x < POS_SPECIAL && (uint64_t)x < segEnd)
     {
       const uint32_t c2 = x / DEC_SCB, off = x - c2 * DEC_SCB;
@@ -392,11 +433,10 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
     {
       const uint32_t c = pos / DEC_SCB, off = pos - c * DEC_SCB;
       if (off < DEC_WIN)
-      {
-        const uint32_t k = c / DEC_SEG;
-        while (ld_volatile_u32(D.flagSeg + k) == 0u) { }
-        __threadfence();
-        pos = __ldcg(D.sufExit + (size_t)c * DEC_WIN + off);
+      { // rows are zeroed per call and an exit is never 0: the entry itself tells whether its segment has published
+        uint32_t v;
+        do { v = ld_volatile_u32(D.sufExit + (size_t)c * DEC_WIN + off); } while (v == 0u);
+        pos = v;
       }
       else pos = dec_sc_exit(D, pos);
     }

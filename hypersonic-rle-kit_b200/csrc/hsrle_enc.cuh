@@ -28,8 +28,9 @@ enum : uint32_t { ST_OK = 0, ST_OVERFLOW = 1, ST_BADSTREAM = 2, ST_BADARG = 3 };
 // ---------------------------------------------------------------- tunables
 constexpr int E1_T = 256;                 // threads per scan macro-tile
 constexpr int E1_WARPS = E1_T / 32;
-constexpr int E1_STEPS = 32;              // 512-byte steps per warp (16 KiB contiguous per warp)
-constexpr int E1_TILE_VECS = E1_T * E1_STEPS;   // 8192 vectors = 128 KiB of input per macro-tile
+constexpr int E1_STEPS = 32;              // at most this many 512-byte steps per warp (16 KiB contiguous per warp); the host picks
+                                          // the count per call so that the tiles fill whole waves of resident CTAs (enc_scan_steps)
+constexpr int E1_TILE_VECS = E1_T * E1_STEPS;   // 8192 vectors = 128 KiB of input per macro-tile at most
 constexpr int E2_T = 128;                 // threads per super-chunk CTA
 constexpr int E2_CH = 4;                  // records per thread
 constexpr int E2_WARM = 12;               // records a thread warms its state guess up on
@@ -101,6 +102,7 @@ struct EncBufs
   const uint8_t *in; uint32_t n;
   uint8_t *out; uint32_t cap;
   uint32_t nVec, nTiles, lastVec;
+  uint32_t scanSteps;                    // E1: 512-byte steps per warp (a tile is E1_T * scanSteps vectors)
   uint32_t maxRuns, maxSC;
   unsigned long long *tileStatus;        // E1 look-back: [2t] aggregate, [2t+1] inclusive prefix: flag(1) | ends(31) | starts(31)
   uint32_t *runA, *runB; void *runSym;   // records: mask run [a,b), first-period symbol (u32 if W <= 4 else u64)

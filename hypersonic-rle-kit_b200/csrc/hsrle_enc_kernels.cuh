@@ -76,14 +76,15 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
   const uint32_t n = B.n, lastVec = B.lastVec;
   const uint8_t *__restrict__ in = B.in;
   const uint4 *in16 = reinterpret_cast<const uint4 *>(in);
-  const uint32_t vw = B.vecBase + tile * E1_TILE_VECS + warp * (32 * E1_STEPS);   // first vector of this warp's span
+  const int steps = (int)B.scanSteps;                  // 512-byte steps per warp in this call (multiple of 4, <= E1_STEPS)
+  const uint32_t vw = B.vecBase + tile * (uint32_t)(E1_T * steps) + warp * (32 * steps);   // first vector of this warp's span
 
   // ---- phase A: masks and per-step totals (no block barrier); loads run one group of 4 steps ahead
   uint32_t c2 = 0, c3 = 0;                 // the 8 input bytes before the current step
   if (lane == 0 && vw >= 1 && vw - 1 <= lastVec) { const uint2 p = __ldg(reinterpret_cast<const uint2 *>(in + (size_t)vw * 16 - 8)); c2 = p.x; c3 = p.y; }
   c2 = __shfl_sync(0xFFFFFFFFu, c2, 0); c3 = __shfl_sync(0xFFFFFFFFu, c3, 0);
   const uint32_t mBeforeSpan = __shfl_sync(0xFFFFFFFFu, (lane == 0) ? m16_generic<W>(in, n, lastVec, (int64_t)vw - 1) : 0u, 0);
-  const uint32_t mAfterSpan = __shfl_sync(0xFFFFFFFFu, (lane == 0) ? m16_generic<W>(in, n, lastVec, (int64_t)vw + 32 * E1_STEPS) : 0u, 0);
+  const uint32_t mAfterSpan = __shfl_sync(0xFFFFFFFFu, (lane == 0) ? m16_generic<W>(in, n, lastVec, (int64_t)vw + 32 * steps) : 0u, 0);
   uint32_t myStepTot = 0;                  // lane j keeps the total of step j
   auto finalize = [&](int j, uint32_t prevLast, uint32_t cur, uint32_t nextFirst)
   {
@@ -103,11 +104,11 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
 #pragma unroll
   for (int k = 0; k < GRP; k++) { const uint32_t v = vw + k * 32 + lane; buf[k] = (v <= lastVec) ? __ldg(in16 + v) : make_uint4(0, 0, 0, 0); }
   uint32_t pendM = 0, pendPrevLast = mBeforeSpan;
-#pragma unroll
-  for (int g = 0; g < E1_STEPS / GRP; g++)
+  const int nGroups = steps / GRP;
+  for (int g = 0; g < nGroups; g++)
   {
     uint4 nxt[GRP];
-    if (g + 1 < E1_STEPS / GRP)
+    if (g + 1 < nGroups)
     {
 #pragma unroll
       for (int k = 0; k < GRP; k++) { const uint32_t v = vw + ((g + 1) * GRP + k) * 32 + lane; nxt[k] = (v <= lastVec) ? __ldg(in16 + v) : make_uint4(0, 0, 0, 0); }
@@ -134,13 +135,13 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
       pl = __shfl_sync(0xFFFFFFFFu, m[k], 31);
     }
     pendM = m[GRP - 1]; pendPrevLast = pl;
-    if (g + 1 < E1_STEPS / GRP)
+    if (g + 1 < nGroups)
     {
 #pragma unroll
       for (int k = 0; k < GRP; k++) buf[k] = nxt[k];
     }
   }
-  finalize(E1_STEPS - 1, pendPrevLast, pendM, mAfterSpan);
+  finalize(steps - 1, pendPrevLast, pendM, mAfterSpan);
   // exclusive scan of the step totals inside the warp
   uint32_t stepInc = myStepTot;
 #pragma unroll
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(E1_T) k_enc_scan(const EncBufs B)
   const uint32_t baseE = (uint32_t)(exclusive >> 31) + (warpBase >> 16);
   SymT *__restrict__ runSym = reinterpret_cast<SymT *>(B.runSym);
   uint32_t *__restrict__ runA = B.runA, *__restrict__ runB = B.runB;
-  for (int j = 0; j < E1_STEPS; j++)
+  for (int j = 0; j < steps; j++)
   {
     const uint32_t stepBase = __shfl_sync(0xFFFFFFFFu, stepExcl, j);
     const uint32_t stepTot = __shfl_sync(0xFFFFFFFFu, myStepTot, j);
@@ -735,7 +736,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
 };
 
 template <int W, int BA, int V, class SymT>
-__global__ void __launch_bounds__(E2_T) k_enc_auto(const EncBufs B, int round)
+__global__ void __launch_bounds__(E2_T, (V == V_LUT3 || V == V_LUT7) ? 4 : 1) k_enc_auto(const EncBufs B, int round)
 {
   using C = EncCta<W, BA, V, SymT>;
   extern __shared__ __align__(16) unsigned char smemRaw[];

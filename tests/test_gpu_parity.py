@@ -193,3 +193,45 @@ def test_full_size_88mb_roundtrip(hs, name):
     rd = hs.decompress_device(name, t_out, r, t_dec, n)
     assert rd == n
     assert torch.equal(t_dec[:n], t_in)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle64_byte_packed", "rle32_3symlut_byte"])
+@pytest.mark.parametrize("kind", ["single_symbol", "random", "alternating", "run_mixed"])
+def test_one_gib_frame_properties(hs, name, kind):
+    """BASELINE configs[4] at the frame size (2^30 bytes, the largest input rle_compress_bounds accepts,
+    src/rle8_extreme_cpu.c:24-25): the oracle is too slow here, so the checks are size-independent properties --
+    header fields, the stream-size bounds the format implies, and the encode -> decode round trip."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 1 << 30
+    g = torch.Generator(device=dev); g.manual_seed(77)
+    if kind == "single_symbol":
+        t_in = torch.full((n,), 0x5A, dtype=torch.uint8, device=dev)
+    elif kind == "random":
+        t_in = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    elif kind == "alternating":
+        t_in = torch.arange(n, dtype=torch.int32, device=dev).bitwise_and_(1).to(torch.uint8)     # 1-byte runs: no candidates for W = 1
+    else:
+        # runs of 1 .. 4096 equal bytes: segment id = cumulative sum of "a new run starts here" flags
+        starts = torch.rand(n, device=dev, generator=g) < (1.0 / 37.0)
+        seg = torch.cumsum(starts.to(torch.int32), 0)
+        del starts
+        t_in = (seg.to(torch.int64) * 2654435761 % 251).to(torch.uint8)
+        del seg
+    codec = CODEC_BY_NAME[name]
+    cap = n + n // 256 + 512
+    t_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    r = hs.compress_device(name, t_in, t_out)
+    assert r > 0, hs.last_error()
+    hdr = t_out[:9].cpu().numpy()
+    assert int.from_bytes(hdr[0:4].tobytes(), "little") == n and int.from_bytes(hdr[4:8].tobytes(), "little") == r
+    if codec.W == 1 and codec.variant in (0, 1):
+        assert hdr[8] == 0                                   # multi mode
+    if kind == "single_symbol":
+        assert r < 64                                        # header + one token + terminator
+    if kind == "random":
+        assert n <= r <= n + n // 256 + 64                   # (almost) one literal; a few accidental short runs at most
+    t_dec = torch.empty(n + 128, dtype=torch.uint8, device=dev)
+    rd = hs.decompress_device(name, t_out, r, t_dec, n)
+    assert rd == n, hs.last_error()
+    assert torch.equal(t_dec[:n], t_in)
