@@ -359,13 +359,20 @@ def run_gpu_arm(args):
     # to move once -- N = uncompressed bytes, C = mean compressed bytes over the codec set
     cavg = csum / len(CODEC_SET)
     alg = {"k_enc_scan": n, "k_enc_auto": None, "k_enc_emit": 2 * cavg, "k_enc_copy_big": None,
-           "k_dec_map": cavg, "k_dec_compose": None, "k_dec_resolve": None, "k_dec_emit": n + cavg, "k_dec_big": None}
+           "k_dec_map": cavg, "k_dec_chain": None, "k_dec_emit": n + cavg, "k_dec_big": None}
     name = top[0]
     alg_bytes = float(alg.get(name) or (n + cavg))     # state-only kernels are charged the whole call (N + C)
     avg_ms = top[1][1] / top[1][0]
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), if one exists
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(name, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "kernel_share_of_step": round(top[1][1] / tot_ms, 4),
+                "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": round(top[1][1] / tot_ms, 4),
                 "whole_pipeline": {"algorithmic_bytes_per_step": 2 * (n * len(CODEC_SET) + csum),
                                    "achieved": round(2 * (n * len(CODEC_SET) + csum) / (ms / args.steps * 1e-3) / 1e9, 1),
                                    "frac": round(2 * (n * len(CODEC_SET) + csum) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},

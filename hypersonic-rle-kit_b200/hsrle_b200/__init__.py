@@ -131,10 +131,19 @@ def decompress_device_async(name, t_in, in_size, t_out, out_size, t_ws, t_result
         raise HsrleError(f"decompress enqueue failed ({rc}): {last_error()}")
 
 
+def _settle(t):
+    """The synchronous device-pointer entry points run on a library-owned stream (include/hsrle_b200.h): whatever the
+    caller still has in flight on the buffers -- here: torch's current stream -- must have finished before the call."""
+    import torch
+    torch.cuda.current_stream(t.device).synchronize()
+
+
 def compress_device(name, t_in, t_out, n=None):
     n = t_in.numel() if n is None else n
+    _settle(t_in)
     return int(lib.hsrle_compress_device(codec_id(name), t_in.data_ptr(), n, t_out.data_ptr(), t_out.numel()))
 
 
 def decompress_device(name, t_in, in_size, t_out, out_size):
+    _settle(t_in)
     return int(lib.hsrle_decompress_device(codec_id(name), t_in.data_ptr(), in_size, t_out.data_ptr(), out_size))

@@ -185,7 +185,9 @@ int hsrle_compress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, 
 int hsrle_decompress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
                                   void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream);
 
-/* Device-resident, synchronous convenience forms (library-owned workspace, returns the byte count). */
+/* Device-resident, synchronous convenience forms (library-owned workspace, returns the byte count).  They run on a
+ * library-owned non-blocking stream: work the caller still has in flight on dIn / dOut (on any of its streams) must
+ * have completed before the call; on return the result is complete. */
 uint32_t hsrle_compress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize);
 uint32_t hsrle_decompress_device(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize);
 

@@ -235,3 +235,35 @@ def test_one_gib_frame_properties(hs, name, kind):
     rd = hs.decompress_device(name, t_out, r, t_dec, n)
     assert rd == n, hs.last_error()
     assert torch.equal(t_dec[:n], t_in)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle16_7symlut_byte", "rle48_3symlut_sym", "rle64_byte"])
+def test_workspace_contents_do_not_matter(hs, name):
+    """The caller-owned workspace of the async entry points may hold anything (another call's tables, another codec's
+    state): only the region the library clears itself is assumed zero."""
+    import torch
+    dev = torch.device("cuda:0")
+    codec = CODEC_BY_NAME[name]
+    data = gen_dct(3 << 20, seed=11)
+    want = oracle_compress(codec, data)
+    n = len(data)
+    cap = out_capacity(n)
+    t_in = torch.from_numpy(data).to(dev)
+    ws = torch.empty(max(hs.compress_workspace_size(name, n), hs.decompress_workspace_size(name, cap, n)), dtype=torch.uint8, device=dev)
+    res = torch.zeros(16, dtype=torch.int32, device=dev)
+    sp = torch.cuda.current_stream().cuda_stream
+    for fill in (0xFF, 0x01, 0x80):
+        ws.fill_(fill)
+        t_out = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        hs.compress_device_async(name, t_in, t_out, ws, res[:8], sp)
+        torch.cuda.synchronize()
+        r = res[:8].tolist()
+        assert r[0] == len(want) and r[1] == 0, (fill, r)
+        assert np.array_equal(t_out[: r[0]].cpu().numpy(), want)
+        ws.fill_(fill)
+        t_dec = torch.zeros(n + 128, dtype=torch.uint8, device=dev)
+        hs.decompress_device_async(name, t_out, r[0], t_dec, n, ws, res[8:], sp)
+        torch.cuda.synchronize()
+        rd = res[8:].tolist()
+        assert rd[0] == n and rd[1] == 0, (fill, rd)
+        assert torch.equal(t_dec[:n], t_in)
