@@ -188,6 +188,12 @@ static bool enc_prepare(int codec, const EncKernels *k)
 {
   std::lock_guard<std::mutex> lk(g_attrMu);
   if (g_attrDone[codec]) return true;
+  // every kernel asks for the same (maximum) shared-memory carve-out: CTAs of kernels with different carve-outs cannot
+  // share an SM, and the calls of several streams are meant to overlap
+  cudaFuncSetAttribute((const void *)k->scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k->autom, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k_enc_copy_big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->autom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->autoSmem), "attr auto")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
   g_attrDone[codec] = true;
@@ -301,6 +307,10 @@ static bool dec_prepare(int codec, const DecKernels *k)
     g_composeAttr = true;
   }
   if (g_dattrDone[codec]) return true;
+  cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k->big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
   g_dattrDone[codec] = true;

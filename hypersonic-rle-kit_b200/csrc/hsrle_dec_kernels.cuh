@@ -148,11 +148,19 @@ constexpr uint32_t DEC_LIN_BYTES = DEC_SCB + 48;
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
 constexpr uint32_t DEC_EXH_ELEMS = DEC_SCB + (DEC_SCB / 64 + 1) * 2;
 
+// The SC image is only read by phase A, which turns it into exit codes front to back, 1 KiB of stream (2112 bytes of
+// table) per step of the CTA: image and table share one buffer, the image at its far end, and a block barrier per step
+// keeps the table's write front below the image's read front (step it writes below 2112 (it + 1) and reads from
+// DM_DATA0 + 1024 it on: DM_DATA0 >= 1088 * 15 + 2112).  35 KB instead of 50 KB per CTA: 6 CTAs per SM instead of 4.
+constexpr uint32_t DM_DATA0 = 18560;
+static_assert(DM_DATA0 % 16 == 0 && DM_DATA0 >= 1088 * (DEC_SCB / 1024 - 1) + 2112, "image must stay ahead of the table");
 struct DecMapSmem
 {
-  alignas(16) uint8_t data[DEC_LIN_BYTES];     // linear SC image (+ the longest token head after it)
-  alignas(16) uint16_t ex[DEC_EXH_ELEMS];
+  alignas(16) uint8_t buf[DM_DATA0 + DEC_LIN_BYTES];
+  __device__ __forceinline__ uint8_t *data() { return buf + DM_DATA0; }                    // linear SC image (+ the longest token head after it)
+  __device__ __forceinline__ uint16_t *ex() { return reinterpret_cast<uint16_t *>(buf); }   // DEC_EXH_ELEMS entries
 };
+static_assert(DEC_EXH_ELEMS * 2 <= DM_DATA0 + DEC_LIN_BYTES, "table fits the buffer");
 constexpr uint32_t DEC_WB = 2048;            // warp-block: the 16 mini-blocks finalised by one warp
 
 // load stream bytes [c0, c0 + DEC_LIN_BYTES) (zero beyond clen), linear -- 16-byte coalesced
@@ -211,13 +219,14 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   const bool single = hs.single != 0;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   uint32_t *farRow = D.farTab + (size_t)c0;
-  dec_load_sc_linear(S.data, D.in, c0, clen);
+  uint16_t *const ex = S.ex();
+  dec_load_sc_linear(S.data(), D.in, c0, clen);
   __syncthreads();
 
   // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
   //      words give the four 24-byte windows); raw code = where that token ends
   {
-    const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.data);
+    const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.data());
     const uint32_t availSC = clen - c0;              // stream bytes from the start of the SC
     for (int it = 0; it < (int)(DEC_SCB / (4 * DM_T)); it++)
     {
@@ -244,8 +253,9 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
         }
         codes[j] = code;
       }
-      uint32_t *dst = reinterpret_cast<uint32_t *>(S.ex + skew16h(p4));
+      uint32_t *dst = reinterpret_cast<uint32_t *>(ex + skew16h(p4));
       dst[0] = codes[0] | (codes[1] << 16); dst[1] = codes[2] | (codes[3] << 16);
+      __syncthreads();                               // table write front vs image read front (DecMapSmem)
     }
   }
   __syncthreads();
@@ -255,8 +265,8 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     const uint32_t h0 = (uint32_t)t * DEC_HB, h1 = h0 + DEC_HB;
     for (uint32_t p = h1; p-- > h0;)
     {
-      uint32_t code = S.ex[skew16h(p)];
-      if (code < h1) { code = S.ex[skew16h(code)]; S.ex[skew16h(p)] = (uint16_t)code; }
+      uint32_t code = ex[skew16h(p)];
+      if (code < h1) { code = ex[skew16h(code)]; ex[skew16h(p)] = (uint16_t)code; }
     }
   }
   __syncthreads();
@@ -264,8 +274,8 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   for (uint32_t i = t; i < DEC_SCB / 2; i += DM_T)
   {
     const uint32_t mb = i / DEC_HB, p = mb * DEC_MB + (i % DEC_HB);
-    const uint32_t code = S.ex[skew16h(p)];
-    if (code < (mb + 1) * DEC_MB) S.ex[skew16h(p)] = S.ex[skew16h(code)];
+    const uint32_t code = ex[skew16h(p)];
+    if (code < (mb + 1) * DEC_MB) ex[skew16h(p)] = ex[skew16h(code)];
   }
   __syncthreads();
   // keep the mini-block table for D3 (eight entries per 16-byte store)
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     uint4 *dst = reinterpret_cast<uint4 *>(D.exTab + (size_t)c * DEC_SCB);
     for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
     {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(S.ex + skew16h(q));
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(ex + skew16h(q));
       dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
     }
   }
@@ -286,11 +296,11 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     {
       uint32_t code[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) code[k] = S.ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)];
+      for (int k = 0; k < 4; k++) code[k] = ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)];
 #pragma unroll
-      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = S.ex[skew16h(code[k])];
+      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = ex[skew16h(code[k])];
 #pragma unroll
-      for (int k = 0; k < 4; k++) S.ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
+      for (int k = 0; k < 4; k++) ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
       __syncwarp();
     }
   }
@@ -300,8 +310,8 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   {
     for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DM_T)
     {
-      uint32_t code = S.ex[skew16h(p)];
-      if (code < DEC_SCB) { code = S.ex[skew16h(code)]; S.ex[skew16h(p)] = (uint16_t)code; }
+      uint32_t code = ex[skew16h(p)];
+      if (code < DEC_SCB) { code = ex[skew16h(code)]; ex[skew16h(p)] = (uint16_t)code; }
     }
     __syncthreads();
   }
@@ -310,12 +320,12 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
     for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
     {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(S.ex + skew16h(q));
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(ex + skew16h(q));
       dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
     }
   }
   // absolute SC exits of the window positions
-  for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = dec_code_pos(S.ex[skew16h(w)], c0, farRow);
+  for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = dec_code_pos(ex[skew16h(w)], c0, farRow);
 }
 
 // ================================================================================================
