@@ -501,6 +501,7 @@ template <int K> struct DecEmitSmem
   DecAgg<K> warpAgg[DX_T / 32 + 1];
   DecAgg<K> bc;
   DecBigOp big[DX_BIGCAP];
+  uint4 lowMask[17];                           // lowMask[i]: the bytes below i of a 16-byte vector
   uint32_t nBig, ticket, flag;
 };
 
@@ -661,14 +662,6 @@ __device__ __forceinline__ uint4 dec_lit_vec_part(const uint8_t *__restrict__ in
   const uint32_t sh = sb * 8;
   return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
 }
-// mask of the bytes of word Kw (bytes 4Kw .. 4Kw+3 of a vector) that lie in [a, b)
-template <int Kw> __device__ __forceinline__ uint32_t dec_byte_mask(uint32_t a, uint32_t b)
-{
-  const int lo = max((int)a - 4 * Kw, 0), hi = min((int)b - 4 * Kw, 4);
-  if (hi <= lo) return 0u;
-  const uint32_t mh = hi >= 4 ? 0xFFFFFFFFu : ((1u << (8 * hi)) - 1u);
-  return mh & ~((1u << (8 * lo)) - 1u);
-}
 // 16 bytes of the period-W pattern `sym` starting at pattern offset ph (0 <= ph < W)
 template <int W> __device__ __forceinline__ uint4 dec_run_vec(uint64_t sym, uint32_t ph)
 {
@@ -725,6 +718,13 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   // status as the kernels before left it: uniform over the grid (errors found here go to sc.emitBad)
   if (sc.status != ST_OK) { dec_emit_done(D, &S.flag); return; }
   if (t == 0) { S.ticket = atomicAdd(&sc.ticket, 1u); S.nBig = 0; }
+  if (t < 17)
+  {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int nb = min(max(t - 4 * k, 0), 4); w[k] = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u); }
+    S.lowMask[t] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   __syncthreads();
   const uint32_t c = S.ticket, c0 = c * DEC_SCB;
   const uint32_t clen = sc.clen, n = sc.n;
@@ -853,44 +853,43 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     //    item passN is the partial vector at the start of the pass (its first bytes belong to the pass / SC before).
     //    A vector is assembled segment by segment: 16 bytes of literal source or run pattern, masked to the segment.
     {
-      auto mixed = [&](uint32_t vb32, uint32_t r0)
-      {
-        const uint64_t vb = vb32;
-        const uint64_t lo = max(vb, (uint64_t)pStart), hi = min(vb + 16, (uint64_t)pEnd);
+      auto mixed = [&](uint32_t vb, uint32_t r0)
+      { // all positions are output offsets <= pEnd <= n: 32-bit arithmetic throughout
+        const uint32_t lo = max(vb, pStart), hi = (vb > 0xFFFFFFEFu || pEnd - vb < 16u) ? pEnd : vb + 16u;
         uint32_t rr = r0;
-        uint64_t tStart = tOut[rr], tNext = tOut[rr + 1];
+        uint32_t tStart = tOut[rr], tNext = tOut[rr + 1];
         uint32_t litLen = tLitLen[rr];
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        uint64_t x = lo;
+        uint32_t x = lo;
         while (x < hi)
         {
           while (x >= tNext) { rr++; tStart = tNext; tNext = tOut[rr + 1]; litLen = tLitLen[rr]; }
-          const uint64_t litEnd = min(tStart + litLen, tNext);
-          uint4 cv; uint64_t segEnd;
+          const uint32_t litEnd = litLen >= tNext - tStart ? tNext : tStart + litLen;
+          uint4 cv; uint32_t segEnd;
           if (x < litEnd)
           {
             segEnd = min(litEnd, hi);
-            cv = dec_lit_vec_part(in, (int64_t)tLitSrc[rr] + (int64_t)vb - (int64_t)tStart, (uint32_t)(x - vb), (uint32_t)(segEnd - vb));
+            cv = dec_lit_vec_part(in, (int64_t)tLitSrc[rr] + ((int64_t)vb - (int64_t)tStart), x - vb, segEnd - vb);
           }
           else
           {
             segEnd = min(tNext, hi);
-            cv = dec_run_vec<W>(tSym[rr], (uint32_t)((vb + 48 - litEnd) % (uint32_t)W));
+            cv = dec_run_vec<W>(tSym[rr], (vb + 48u - litEnd) % (uint32_t)W);     // small and positive even if vb + 48 wraps
           }
-          const uint32_t a = (uint32_t)(x - vb), b = (uint32_t)(segEnd - vb);
-          a0 |= cv.x & dec_byte_mask<0>(a, b); a1 |= cv.y & dec_byte_mask<1>(a, b);
-          a2 |= cv.z & dec_byte_mask<2>(a, b); a3 |= cv.w & dec_byte_mask<3>(a, b);
+          const uint4 mb = S.lowMask[segEnd - vb], ma = S.lowMask[x - vb];   // bytes [x, segEnd) of the vector
+          a0 |= cv.x & mb.x & ~ma.x; a1 |= cv.y & mb.y & ~ma.y;
+          a2 |= cv.z & mb.z & ~ma.z; a3 |= cv.w & mb.w & ~ma.w;
           x = segEnd;
         }
-        if (lo == vb && hi == vb + 16) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(a0, a1, a2, a3);
+        if (lo == vb && hi - vb == 16u) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(a0, a1, a2, a3);
         else
         {
-          const uint32_t ba = (uint32_t)(lo - vb), bb = (uint32_t)(hi - vb);
+          const uint32_t ba = lo - vb, bb = hi - vb;
 #pragma unroll
           for (int i = 0; i < 16; i++)
           {
             const uint32_t wv = (i >> 2) == 0 ? a0 : (i >> 2) == 1 ? a1 : (i >> 2) == 2 ? a2 : a3;
-            if ((uint32_t)i >= ba && (uint32_t)i < bb) out[vb + i] = (uint8_t)(wv >> (8 * (i & 3)));
+            if ((uint32_t)i >= ba && (uint32_t)i < bb) out[(size_t)vb + i] = (uint8_t)(wv >> (8 * (i & 3)));
           }
         }
       };
