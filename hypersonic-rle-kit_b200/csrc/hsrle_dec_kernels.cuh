@@ -649,15 +649,14 @@ __device__ __forceinline__ uint4 dec_lit_vec(const uint8_t *__restrict__ in, uin
 // not read (they may lie before the stream or after its end), `src` may be negative
 __device__ __forceinline__ uint4 dec_lit_vec_part(const uint8_t *__restrict__ in, int64_t src, uint32_t a, uint32_t b)
 {
-  const uint32_t sb = (uint32_t)(src & 3);
-  const int64_t wb = src - sb;                     // aligned stream offset of word 0
-  const int64_t s0 = src + a, s1 = src + b;         // needed stream bytes [s0, s1)
+  const uint32_t sb = (uint32_t)src & 3u;
+  const uint8_t *base = in + (src - (int64_t)sb);                  // aligned stream position of word 0
   uint32_t w[5];
 #pragma unroll
   for (int k = 0; k < 5; k++)
-  {
-    const int64_t q = wb + 4 * k;
-    w[k] = (q < s1 && q + 4 > s0) ? __ldg(reinterpret_cast<const uint32_t *>(in + q)) : 0u;
+  { // word k holds the vector bytes [4k - sb, 4k - sb + 4)
+    const int v0 = 4 * k - (int)sb;
+    w[k] = (v0 < (int)b && v0 + 4 > (int)a) ? __ldg(reinterpret_cast<const uint32_t *>(base + 4 * k)) : 0u;
   }
   const uint32_t sh = sb * 8;
   return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));

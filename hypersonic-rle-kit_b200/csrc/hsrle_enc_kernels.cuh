@@ -801,18 +801,21 @@ __device__ __forceinline__ void copy_bytes_warp(uint8_t *dst, const uint8_t *src
 
 constexpr int E3_NDESC = E2_SCR;
 constexpr uint32_t E3_PIECE = 16;         // bytes per flattened literal piece
-constexpr uint32_t E3_STAGE = 32768;      // stream bytes of a super-chunk that can be staged in shared memory
-constexpr uint32_t E3_NPIECE = E3_STAGE / E3_PIECE + E3_NDESC + 8;
+// stream bytes of a super-chunk that can be staged in shared memory.  Wider symbols mean fewer but longer tokens: the 512
+// tokens of a 32-bit super-chunk carry ~32 KB on the DCT stream (measured: E3 70 -> 35 us with the 64 KB stage); 24-bit
+// super-chunks fit 32 KB, and from 48 bits on most literals are long enough for the grid-wide copy kernel anyway
+HSRLE_HDC uint32_t e3_stage(int W) { return W == 4 ? 65536u : 32768u; }
+HSRLE_HDC uint32_t e3_npiece(int W) { return e3_stage(W) / E3_PIECE + E3_NDESC + 8; }
 
 template <int W, int BA, int V, class SymT> struct EncEmitSmem
 {
   using C = EncCta<W, BA, V, SymT>;
-  alignas(16) uint8_t stage[E3_STAGE + 32];
+  alignas(16) uint8_t stage[e3_stage(W) + 32];
   uint32_t a[C::NSLOT], b[C::NSLOT];
   SymT sym[C::NSLOT];
   EmitDesc desc[E3_NDESC];
   uint32_t pieceOff[E3_NDESC + 1];
-  uint16_t pieceDesc[E3_NPIECE];
+  uint16_t pieceDesc[e3_npiece(W)];
   unsigned long long warpTot[E2_T / 32];
   uint32_t warpTot32[E2_T / 32];
   uint32_t nDesc;
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     for (int w = 0; w < E2_T / 32; w++) { const unsigned long long x = S.warpTot[w]; if (w < warp) pre += x; segLen += x; }
     const uint64_t seg0 = (uint64_t)B.outBase + B.scBase[s];
     uint64_t pos = seg0 + pre + (inc - mine);
-    const bool staged = segLen <= E3_STAGE;            // uniform
+    const bool staged = segLen <= e3_stage(W);         // uniform
     const uint32_t shift = (uint32_t)(seg0 & 15);      // keeps stage image and stream equally aligned
     // pass 2: headers, literal descriptors
     if (active)
@@ -948,25 +951,43 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     __syncthreads();
     if (staged)
     {
-      for (uint32_t i = t; i < totalPieces; i += E2_T)
+      // four pieces per thread and step: the (up to 20) source words of a step are in flight together
+      constexpr int E3_MLP = 4;
+      for (uint32_t i0 = t; i0 < totalPieces; i0 += E2_T * E3_MLP)
       {
-        const uint32_t a = S.pieceDesc[i];
-        const EmitDesc e = S.desc[a];
-        const uint32_t off = (i - S.pieceOff[a]) * E3_PIECE;
-        const uint32_t len = min(E3_PIECE, e.len - off);
-        const uint8_t *src = in + e.src + off;
-        const uint32_t sb = (uint32_t)((uintptr_t)src & 3);
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
-        const uint32_t need = sb + len;             // bytes needed from the aligned word stream
-        uint32_t w[5];
+        uint32_t w[E3_MLP][5], dstOff[E3_MLP], len[E3_MLP], sb[E3_MLP];
 #pragma unroll
-        for (int k = 0; k < 5; k++) w[k] = ((uint32_t)k * 4 < need) ? __ldg(sw + k) : 0u;
-        uint32_t o[4];
+        for (int u = 0; u < E3_MLP; u++)
+        {
+          const uint32_t i = i0 + u * E2_T;
+          len[u] = 0; dstOff[u] = 0; sb[u] = 0;
+          const uint32_t *sw = reinterpret_cast<const uint32_t *>(in);
+          uint32_t need = 0;
+          if (i < totalPieces)
+          {
+            const uint32_t a = S.pieceDesc[i];
+            const EmitDesc e = S.desc[a];
+            const uint32_t off = (i - S.pieceOff[a]) * E3_PIECE;
+            len[u] = min(E3_PIECE, e.len - off);
+            const uint8_t *src = in + e.src + off;
+            sb[u] = (uint32_t)((uintptr_t)src & 3);
+            sw = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
+            need = sb[u] + len[u];                    // bytes needed from the aligned word stream
+            dstOff[u] = e.dst + off;
+          }
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sb * 8);
-        uint8_t *dst = S.stage + e.dst + off;
+          for (int k = 0; k < 5; k++) w[u][k] = ((uint32_t)k * 4 < need) ? __ldg(sw + k) : 0u;
+        }
 #pragma unroll
-        for (uint32_t k = 0; k < E3_PIECE; k++) if (k < len) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        for (int u = 0; u < E3_MLP; u++)
+        {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(w[u][k], w[u][k + 1], sb[u] * 8);
+          uint8_t *dst = S.stage + dstOff[u];
+#pragma unroll
+          for (uint32_t k = 0; k < E3_PIECE; k++) if (k < len[u]) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+        }
       }
       __syncthreads();
       // flush the image: bytes [shift, shift + segLen) of the stage go to stream bytes [seg0, seg0 + segLen)
