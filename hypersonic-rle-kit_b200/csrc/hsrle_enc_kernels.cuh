@@ -245,28 +245,24 @@ template <int W, int BA, int V, class SymT> struct EncCta
   using Seg = SegSum<K>;
   static constexpr int NREC = E2_SCR + E2_WARM;               // with the warm-up halo
   static constexpr int NSLOT = NREC + NREC / E2_CH + 1;
-  // LUT codecs: one warp per super-chunk, E2L_CH records per lane (the scan element carries the LUT aggregate, so a
-  // 32-element warp scan instead of a 128-element block scan is what makes them affordable)
+  // one warp per super-chunk, E2L_CH records per lane: a 32-element warp scan per fixed-point step, no block barrier
+  // (LUT codecs: the scan element carries the 7-entry LUT aggregate; plain/packed: 2.6x fewer instructions than four
+  // records per thread with block scans)
   static constexpr int NW = E2_T / 32;
   static constexpr int NSLOTL = NREC + NREC / E2L_CH + 2;
 
-  struct CtaRecs
-  {
-    uint32_t a[NSLOT], b[NSLOT];
-    SymT sym[NSLOT];
-    AutoState serSt[E2_T];                                      // states produced by the in-CTA sequential pass
-  };
   struct WarpRecs
   {
     uint32_t a[NSLOTL], b[NSLOTL];
     SymT sym[NSLOTL];
-    AutoState serSt[32]; Lut serLut[32];
+    AutoState serSt[32]; Lut serLut[K ? 32 : 1];               // states produced by the sequential pass
+    AutoState snap[K ? 1 : 32][E2L_CH / E2_CH];                 // plain/packed: per lane, the state at every E3 chunk boundary
     uint64_t fo[8];
     uint32_t foMiss, sens;
   };
   struct Smem
   {
-    typename std::conditional<K != 0, WarpRecs[NW], CtaRecs>::type r;
+    WarpRecs r[NW];
     Seg warpTot[E2_T / 32];
     Seg bcTot;
     AutoState bcSt; Lut bcLut;                                  // broadcast slots
@@ -279,13 +275,14 @@ template <int W, int BA, int V, class SymT> struct EncCta
   // only then can the range's decisions depend on the table it started from (hsrle_enc.cuh)
   template <int CHS>
   static __device__ __forceinline__ Seg eval_range(const uint32_t *ra, const uint32_t *rb, const SymT *rs, uint32_t n, uint32_t floor, int j0, int j1,
-                                                   AutoState &st, Lut &lut, uint32_t *sens0 = nullptr)
+                                                   AutoState &st, Lut &lut, uint32_t *sens0 = nullptr, AutoState *snap = nullptr)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     Seg r = segsum_identity<K>();
     uint32_t fl = 0, known = 0, sens = 0;
     for (int j = j0; j < j1; j++)
     {
+      if (snap && ((j - j0) & (E2_CH - 1)) == 0) snap[(j - j0) / E2_CH] = st;      // state at every E3 chunk boundary
       const int q = j + j / CHS;
       uint32_t s, e; CountSink h;
       const uint32_t lastBefore = st.last;
@@ -338,102 +335,9 @@ template <int W, int BA, int V, class SymT> struct EncCta
     return d;
   }
 
-  // One super-chunk.  given == true: (gSt,gLut) is the incoming state to use for the first chunk;
-  // otherwise it is guessed by warming up over the halo chunk.  Writes the per-chunk incoming states,
-  // the super-chunk summary and (when guessed) the assumed incoming state.
-  template <int KK = K>
-  static __device__ typename std::enable_if<KK == 0>::type process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
-  {
-    constexpr Spec sp = make_spec(W, BA, V);
-    const uint32_t nRuns = B.sc->nRuns, n = B.n, floor = B.sliceLo, endShift = B.sc->endShift;
-    const uint32_t lo = s * E2_SCR;
-    const uint32_t cnt = min((uint32_t)E2_SCR, nRuns - lo);
-    const int halo = (s > 0) ? E2_WARM : 0;
-    const SymT *runSym = reinterpret_cast<const SymT *>(B.runSym);
-    __syncthreads();   // previous users of the shared arrays are done
-    for (int j = threadIdx.x + (E2_WARM - halo); j < E2_WARM + (int)cnt; j += E2_T)
-    {
-      const uint32_t g = lo + j - E2_WARM;
-      const int q = rec_slot(j);
-      S.r.a[q] = B.runA[g]; S.r.b[q] = B.runB[g + endShift]; S.r.sym[q] = runSym[g];
-    }
-    __syncthreads();
-    const int t = threadIdx.x;
-    const int j0 = E2_WARM + t * E2_CH;
-    const int j1 = min(j0 + E2_CH, E2_WARM + (int)cnt);
-    const bool active = j0 < j1;
-
-    AutoState stIn; Lut lutIn;
-    if (t == 0 && given) { stIn = gSt; lutIn = gLut; }
-    else if (t == 0 && s == 0) enc_stream_incoming(B, W, stIn, lutIn);
-    else
-    { // warm up over the preceding E2_WARM records from the neutral guess
-      const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
-      enc_neutral_state(sp, (active && w0 < j0) ? S.r.a[rec_slot(w0)] : 0u, stIn, lutIn);
-      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
-    }
-    Seg mine = segsum_identity<K>();
-    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut); }
-
-    // fixed point of (scan -> compare -> re-run)
-    AutoState st0; Lut lut0;   // incoming state of the super-chunk = what thread 0 used
-    if (t == 0) { S.bcSt = stIn; S.bcLut = lutIn; }
-    __syncthreads();
-    st0 = S.bcSt; lut0 = S.bcLut;
-    Seg total;
-    bool converged = false;
-    for (int it = 0; it < E2_MAXIT; it++)
-    {
-      const Seg pre = block_excl_scan(S, mine, total);
-      AutoState want = st0; Lut wantLut = lut0;
-      segsum_apply<K>(want, wantLut, pre);
-      int changed = 0;
-      if (active && t > 0 && state_differs(want, wantLut, stIn, lutIn))
-      {
-        stIn = want; lutIn = wantLut; changed = 1;
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut);
-      }
-      if (!__syncthreads_or(changed)) { converged = true; break; }
-    }
-    if (!converged)
-    { // exact in-CTA sequential pass: thread 0 threads the state through every chunk
-      if (t == 0)
-      {
-        AutoState st = st0; Lut lut = lut0;
-        for (int c = 0; c * E2_CH < (int)cnt; c++)
-        {
-          S.r.serSt[c] = st;
-          const int a0 = E2_WARM + c * E2_CH, a1 = min(a0 + E2_CH, E2_WARM + (int)cnt);
-          (void)eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, a0, a1, st, lut);
-        }
-        atomicAdd(&B.sc->innerSerial, 1u);
-      }
-      __syncthreads();
-      if (active)
-      {
-        stIn = S.r.serSt[t];
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2_CH>(S.r.a, S.r.b, S.r.sym, n, floor, j0, j1, st, lut);
-      }
-      (void)block_excl_scan(S, mine, total);
-    }
-    // publish
-    if (active)
-    {
-      const uint32_t chunk = s * E2_T + t;
-      B.cIn[chunk] = stIn;
-      if (K) B.cLut[chunk] = lutIn;
-    }
-    if (t == 0)
-    {
-      B.scSum[s] = total.cs; if (K) B.scAgg[s] = total.agg;
-      B.scBytes[s] = total.bytes; B.scTok[s] = total.ntok;
-      if (!given) { B.scIn[s] = st0; if (K) B.scLut[s] = lut0; }
-    }
-    totalOut = total;
-  }
-
-
-  // ---- LUT codecs: one super-chunk per WARP.  Same contract as the CTA variant; additionally publishes what the
+  // ---- One super-chunk per WARP, E2L_CH records per lane.  given == true: (gSt,gLut) is the incoming state to use;
+  //      otherwise it is guessed by warming up over the halo records.  Writes the per-chunk incoming states (E3), the
+  //      super-chunk summary and (when guessed) the assumed incoming state.  LUT codecs additionally publish what the
   //      sensitivity scheme needs (hsrle_enc.cuh: enc_fo_misses / enc_chunk_lut): scFo, scFlags, cKnown, and scBytes
   //      without the symbol bytes of the first emissions.
   static __device__ __forceinline__ void warp_scan(const Seg &mine, Seg &pre, Seg &total)
@@ -451,8 +355,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     total = shfl_idx_t(inc, 31);
   }
 
-  template <int KK = K>
-  static __device__ typename std::enable_if<KK != 0>::type process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
+  static __device__ void process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     const int lane = threadIdx.x & 31;
@@ -486,9 +389,11 @@ template <int W, int BA, int V, class SymT> struct EncCta
     }
     Seg mine = segsum_identity<K>();
     uint32_t sens0 = 0;
-    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0); }
+    AutoState *const snapP = K ? nullptr : R.snap[K ? 0 : lane];   // plain/packed: the chunk states E3 needs fall out of the last evaluation
+    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP); }
     const AutoState st0 = shfl_idx_t(stIn, 0);
-    const Lut lut0 = shfl_idx_t(lutIn, 0);
+    Lut lut0;
+    if constexpr (K != 0) lut0 = shfl_idx_t(lutIn, 0); else lut_init(lut0, W);
 
     // fixed point of (scan -> compare -> re-run).  A lane whose decisions cannot depend on the table it started from
     // (sens0 == 0) only takes the exact table; its summary stands (its byte count is redone by the final pass).
@@ -506,7 +411,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         if (want != stIn || (lutDiff && sens0))
         {
           stIn = want; lutIn = wantLut; changed = 1;
-          AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0);
+          AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP);
         }
         else if (lutDiff) lutIn = wantLut;
       }
@@ -519,7 +424,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         AutoState st = st0; Lut lut = lut0;
         for (int c = 0; c * E2L_CH < (int)cnt; c++)
         {
-          R.serSt[c] = st; R.serLut[c] = lut;
+          R.serSt[c] = st; if (K) R.serLut[K ? c : 0] = lut;
           const int a0 = E2_WARM + c * E2L_CH, a1 = min(a0 + E2L_CH, E2_WARM + (int)cnt);
           (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, a0, a1, st, lut);
         }
@@ -528,13 +433,22 @@ template <int W, int BA, int V, class SymT> struct EncCta
       __syncwarp();
       if (active)
       {
-        stIn = R.serSt[lane]; lutIn = R.serLut[lane];
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut);
+        stIn = R.serSt[lane]; if (K) lutIn = R.serLut[K ? lane : 0];
+        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, nullptr, snapP);
       }
       warp_scan(mine, pre, total);
     }
-    // final pass: per-chunk incoming states for E3, sensitivity, first emissions
-    if (active)
+    // final pass (LUT codecs): per-chunk incoming states for E3, sensitivity, first emissions
+    if constexpr (K == 0)
+    {
+      if (active)
+      {
+#pragma unroll
+        for (int c = 0; c < E2L_CH / E2_CH; c++)
+          if (j0 + c * E2_CH < j1) B.cIn[s * E2_T + (uint32_t)(j0 - E2_WARM) / E2_CH + c] = snapP[c];
+      }
+    }
+    else if (active)
     {
       AutoState st = stIn; Lut lut = lutIn;
       uint32_t known = pre.agg.m, sensL = 0;
@@ -544,24 +458,29 @@ template <int W, int BA, int V, class SymT> struct EncCta
         if (((j - j0) & (E2_CH - 1)) == 0)
         {
           const uint32_t chunk = s * E2_T + (uint32_t)(j - E2_WARM) / E2_CH;
-          B.cIn[chunk] = st; B.cLut[chunk] = lut; B.cKnown[chunk] = (uint8_t)known;
+          B.cIn[chunk] = st;
+          if (K) { B.cLut[chunk] = lut; B.cKnown[chunk] = (uint8_t)known; }
         }
         const int q = j + j / E2L_CH;
         uint32_t rs, re; CountSink h;
         const uint32_t lastBefore = st.last;
         const uint32_t ev = enc_eval(sp, (uint64_t)R.sym[q], n, R.a[q], R.b[q], st, lut, nullptr, rs, re, h);
         if (ev & EV_EMIT) bytesL += h.len + slice_lit_len(lastBefore, rs, floor);
-        const uint32_t idx = (ev >> EV_IDX_SHIFT) & 7u;
-        if ((ev & EV_VALID) && known < (uint32_t)K && idx >= known)
+        if constexpr (K != 0)
         {
-          if (ev & EV_MARG) sensL = 1;
-          if (ev & EV_EMIT) { R.fo[known] = lut.s[0]; if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
+          const uint32_t idx = (ev >> EV_IDX_SHIFT) & 7u;
+          if ((ev & EV_VALID) && known < (uint32_t)K && idx >= known)
+          {
+            if (ev & EV_MARG) sensL = 1;
+            if (ev & EV_EMIT) { R.fo[known] = lut.s[0]; if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
+          }
         }
       }
       if (sensL) R.sens = 1;
       mine.bytes = bytesL;
     }
     else mine.bytes = 0;
+    if constexpr (K != 0)
     { // exact (under the incoming table this run used) token bytes of the super-chunk
       uint64_t b = mine.bytes;
 #pragma unroll
@@ -571,13 +490,17 @@ template <int W, int BA, int V, class SymT> struct EncCta
     __syncwarp();
     if (lane == 0)
     {
-      B.scSum[s] = total.cs; B.scAgg[s] = total.agg;
+      B.scSum[s] = total.cs;
       B.scBytes[s] = total.bytes - (uint64_t)W * R.foMiss; B.scTok[s] = total.ntok;
-      Lut fo;
+      if constexpr (K != 0)
+      {
+        B.scAgg[s] = total.agg;
+        Lut fo;
 #pragma unroll
-      for (int i = 0; i < 7; i++) fo.s[i] = (i < K && i < (int)total.agg.m) ? R.fo[i] : 0ull;
-      B.scFo[s] = fo; B.scFlags[s] = R.sens ? (uint8_t)SCF_SENS : (uint8_t)0;
-      if (!given) { B.scIn[s] = st0; B.scLut[s] = lut0; }
+        for (int i = 0; i < 7; i++) fo.s[i] = (i < K && i < (int)total.agg.m) ? R.fo[i] : 0ull;
+        B.scFo[s] = fo; B.scFlags[s] = R.sens ? (uint8_t)SCF_SENS : (uint8_t)0;
+      }
+      if (!given) { B.scIn[s] = st0; if (K) B.scLut[s] = lut0; }
       __threadfence();                                            // read by the round's last CTA
     }
     totalOut = total;
@@ -712,13 +635,9 @@ template <int W, int BA, int V, class SymT> struct EncCta
       __syncthreads();
       if (need)
       {
-        if (K)
-        {
-          if (warp == 0) { process(B, S, s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
-          __syncthreads();
-          tot = S.bcTot;
-        }
-        else process(B, S, s, true, run, runLut, tot);
+        if (warp == 0) { process(B, S, s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
+        __syncthreads();
+        tot = S.bcTot;
         if (t == 0) { B.scIn[s] = run; if (K) B.scLut[s] = runLut; B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
       }
       else
@@ -744,8 +663,8 @@ __global__ void __launch_bounds__(E2_T, (V == V_LUT3 || V == V_LUT7) ? 4 : 1) k_
   EncScalars &sc = *B.sc;
   if (round > 0 && sc.nDirty[round - 1] == 0) return;
   const uint32_t nSC = sc.nSC;
-  constexpr int SCS_PER_CTA = C::K ? C::NW : 1;                        // LUT codecs: one super-chunk per warp
-  const uint32_t sFirst = C::K ? blockIdx.x * SCS_PER_CTA + (threadIdx.x >> 5) : blockIdx.x;
+  constexpr int SCS_PER_CTA = C::NW;                                   // one super-chunk per warp
+  const uint32_t sFirst = blockIdx.x * SCS_PER_CTA + (threadIdx.x >> 5);
   for (uint32_t s = sFirst; s < nSC; s += gridDim.x * SCS_PER_CTA)
   {
     typename C::Seg tot;
