@@ -123,7 +123,7 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   B.runA = cv.take<uint32_t>(B.maxRuns); B.runB = cv.take<uint32_t>(B.maxRuns);
   B.runSym = cv.take<uint64_t>(sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns);
   B.cIn = cv.take<AutoState>(maxChunks); B.cLut = cv.take<Lut>(sp.K ? maxChunks : 1); B.cKnown = cv.take<uint8_t>(sp.K ? maxChunks : 1);
-  B.scFo = cv.take<Lut>(sp.K ? B.maxSC : 1); B.scFlags = cv.take<uint8_t>(sp.K ? B.maxSC : 1);
+  B.scFo = cv.take<Lut>(sp.K ? B.maxSC : 1); B.scFlags = cv.take<uint8_t>(sp.K ? B.maxSC : 1); B.scQ = cv.take<ScQueries>(sp.K ? B.maxSC : 1);
   B.scIn = cv.take<AutoState>(B.maxSC); B.scLut = cv.take<Lut>(sp.K ? B.maxSC : 1);
   B.scSum = cv.take<ChunkSum>(B.maxSC); B.scAgg = cv.take<LutAgg>(sp.K ? B.maxSC : 1);
   B.scBytes = cv.take<uint64_t>(B.maxSC); B.scTok = cv.take<uint32_t>(B.maxSC); B.scBase = cv.take<uint64_t>(B.maxSC);
@@ -217,7 +217,7 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
   const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
-  for (int r = 0; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+  for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
@@ -277,11 +277,11 @@ static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
       break;
     case 1:   // boundary-run fix-up, automaton from the assumed incoming state
       HSRLE_LAUNCH(k_enc_slice_link, 1, 32, 0, st, B, sp);
-      for (int r = 0; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
       break;
     case 2:   // true incoming state, repair rounds
       HSRLE_LAUNCH(k_enc_slice_inject, 1, 32, 0, st, B, sp);
-      for (int r = 1; r < E2_ROUNDS; r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      for (int r = 1; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
       break;
     case 3:   // tokens
       HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);

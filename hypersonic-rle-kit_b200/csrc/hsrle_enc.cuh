@@ -40,6 +40,11 @@ static_assert(E2L_CH * 32 == E2_SCR && E2L_CH % E2_CH == 0, "a warp covers one s
 constexpr uint32_t SCF_SENS = 1;          // scFlags: a decision of the super-chunk depended on the incoming LUT
 constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
 constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
+constexpr int E2L1_ROUNDS = 24;           // ... for the 8-bit LUT codecs, whose table has long-range memory:
+                                          // a changed table travels one super-chunk per round; rounds without dirt return at once
+constexpr int E2_MAXROUNDS = 24;
+HSRLE_HDC int enc_rounds(int W, int K) { return (K != 0 && W == 1) ? E2L1_ROUNDS : E2_ROUNDS; }
+constexpr int E2_NQ = 6;                  // LUT codecs: recorded table queries per super-chunk (more: always re-run)
 constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
 constexpr uint32_t BIG_COPY = 65536;      // ... and these are split over the whole grid
 
@@ -48,9 +53,9 @@ struct EncScalars
 {
   uint32_t tileTicket;                    // E1 dynamic tile ids
   uint32_t nRuns, nSC;
-  uint32_t done[E2_ROUNDS];               // E2 per-round "CTAs finished" counters
-  uint32_t nDirty[E2_ROUNDS];
-  uint32_t firstDirty[E2_ROUNDS];
+  uint32_t done[E2_MAXROUNDS];            // E2 per-round "CTAs finished" counters
+  uint32_t nDirty[E2_MAXROUNDS];
+  uint32_t firstDirty[E2_MAXROUNDS];
   uint32_t status;
   uint32_t total;                         // final stream size
   uint32_t nTok;
@@ -63,6 +68,17 @@ struct EncScalars
 };
 
 struct CopyDesc { uint32_t dst, src, len; };
+
+// LUT codecs: the decisions of a super-chunk that consulted the part of the table it inherited (marginal candidates whose
+// symbol had not been emitted inside the super-chunk yet): symbol, how many first emissions (scFo) preceded it, and the
+// answer it got.  The super-chunk's evaluation stays valid under another incoming table iff every answer stays the same.
+struct ScQueries
+{
+  uint32_t n;                             // queries met (only the first E2_NQ are recorded)
+  uint8_t known[8], hit[8];
+  uint32_t pad;
+  uint64_t sym[E2_NQ];
+};
 
 struct ChunkSum
 {
@@ -112,6 +128,7 @@ struct EncBufs
   ChunkSum *scSum; LutAgg *scAgg;        // per super-chunk: summary under the current decisions
   uint64_t *scBytes; uint32_t *scTok;    // per super-chunk: token bytes (LUT codecs: without the symbol bytes of scFo) / tokens
   Lut *scFo; uint8_t *scFlags;           // LUT codecs: symbols in order of first emission (scAgg.m of them), SCF_* flags
+  ScQueries *scQ;                        // LUT codecs: the table queries behind SCF_SENS
   uint64_t *scBase;                      // per super-chunk: exclusive token-byte offset
   uint8_t *scDirty;
   CopyDesc *bigList, *medList;
@@ -224,6 +241,25 @@ HSRLE_HD uint32_t enc_fo_misses(const Lut &fo, uint32_t m, int K, const Lut &inc
     }
   }
   return misses;
+}
+// would any recorded query of a super-chunk get another answer if its incoming table were `incoming`?
+HSRLE_HD bool enc_queries_differ(const ScQueries &q, const Lut &fo, uint32_t m, int K, const Lut &incoming)
+{
+  if (q.n > (uint32_t)E2_NQ) return true;
+  Lut l = incoming;
+  bool diff = false;
+  HSRLE_UNROLL
+  for (int k = 0; k < 7; k++)
+  {
+    if (k < K)
+    { // l = incoming table after the first k first-emissions
+      HSRLE_UNROLL
+      for (int i = 0; i < E2_NQ; i++)
+        if ((uint32_t)i < q.n && q.known[i] == (uint8_t)k) diff = diff || ((lut_find(l, K, q.sym[i]) != K) != (q.hit[i] != 0));
+      if (k < (int)m) { const int idx = lut_find(l, K, fo.s[k]); lut_touch(l, K, idx, fo.s[k]); }
+    }
+  }
+  return diff;
 }
 // exact incoming table of a chunk: its `known` leading entries, then the super-chunk's exact incoming table
 HSRLE_HD void enc_chunk_lut(Lut &chunkLut, uint32_t known, int K, const Lut &scIncoming)

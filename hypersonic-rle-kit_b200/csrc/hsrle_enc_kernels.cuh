@@ -259,6 +259,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     AutoState snap[K ? 1 : 32][E2L_CH / E2_CH];                 // plain/packed: per lane, the state at every E3 chunk boundary
     uint64_t fo[8];
     uint32_t foMiss, sens;
+    ScQueries q;
   };
   struct Smem
   {
@@ -372,7 +373,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       const int q = j + j / E2L_CH;
       R.a[q] = B.runA[g]; R.b[q] = B.runB[g + endShift]; R.sym[q] = runSym[g];
     }
-    if (lane == 0) { R.foMiss = 0; R.sens = 0; }
+    if (lane == 0) { R.foMiss = 0; R.sens = 0; R.q.n = 0; }
     __syncwarp();
     const int j0 = E2_WARM + lane * E2L_CH;
     const int j1 = min(j0 + E2L_CH, E2_WARM + (int)cnt);
@@ -471,7 +472,16 @@ template <int W, int BA, int V, class SymT> struct EncCta
           const uint32_t idx = (ev >> EV_IDX_SHIFT) & 7u;
           if ((ev & EV_VALID) && known < (uint32_t)K && idx >= known)
           {
-            if (ev & EV_MARG) sensL = 1;
+            if (ev & EV_MARG)
+            { // a decision that consulted the inherited part of the table: record the query
+              sensL = 1;
+              const uint32_t slot = atomicAdd(&R.q.n, 1u);
+              if (slot < (uint32_t)E2_NQ)
+              {
+                R.q.sym[slot] = (ev & EV_EMIT) ? lut.s[0] : sym_rot((uint64_t)R.sym[q], W, rs - (R.a[q] - W));
+                R.q.known[slot] = (uint8_t)known; R.q.hit[slot] = idx < (uint32_t)K ? 1 : 0;
+              }
+            }
             if (ev & EV_EMIT) { R.fo[known] = lut.s[0]; if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
           }
         }
@@ -499,6 +509,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
 #pragma unroll
         for (int i = 0; i < 7; i++) fo.s[i] = (i < K && i < (int)total.agg.m) ? R.fo[i] : 0ull;
         B.scFo[s] = fo; B.scFlags[s] = R.sens ? (uint8_t)SCF_SENS : (uint8_t)0;
+        B.scQ[s] = R.q;
       }
       if (!given) { B.scIn[s] = st0; if (K) B.scLut[s] = lut0; }
       __threadfence();                                            // read by the round's last CTA
@@ -555,6 +566,13 @@ template <int W, int BA, int V, class SymT> struct EncCta
     if (fOk) { const uint32_t src = fin.last; for (uint32_t k = threadIdx.x; k < fLen; k += blockDim.x) B.out[fPos + k] = B.in[src + k]; }
   }
 
+  // would super-chunk s decide anything differently if its incoming table were `lut`?
+  static __device__ __forceinline__ bool lut_sensitive(const EncBufs &B, uint32_t s, const Lut &lut)
+  {
+    if (!K || !(B.scFlags[s] & SCF_SENS)) return false;
+    return enc_queries_differ(B.scQ[s], B.scFo[s], B.scAgg[s].m, K, lut);
+  }
+
   // exact token bytes of super-chunk s when its incoming table is `lut`
   static __device__ __forceinline__ uint64_t sc_bytes(const EncBufs &B, uint32_t s, const Lut &lut)
   {
@@ -590,7 +608,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     {
       bool bad = false;
       if (B.scIn[s] != st) { B.scIn[s] = st; bad = true; }
-      if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; if (B.scFlags[s] & SCF_SENS) bad = true; }
+      if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; if (lut_sensitive(B, s, lut)) bad = true; }
       B.scDirty[s] = bad ? 1 : 0;
       if (bad) { if (!nd) first = s; nd++; }
       B.scBase[s] = bytes;                       // relative to the thread's first super-chunk until (3)
@@ -615,7 +633,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     AutoState fin; Lut finLut; enc_stream_incoming(B, W, fin, finLut);
     segsum_apply<K>(fin, finLut, total);
     if (nDirty == 0) { finish(B, fin, finLut, totalBytes, total.ntok); return; }
-    if (round < E2_ROUNDS - 1) return;
+    if (round < enc_rounds(W, K) - 1) return;
 
     // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
     // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA / one warp each)
@@ -631,7 +649,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       Seg tot;
       bool need = B.scDirty[s] != 0 || B.scIn[s] != run;               // uniform: every thread reads the same words
       const bool lutDiff = K && !lut_equal(B.scLut[s], runLut, K);
-      if (lutDiff && (B.scFlags[s] & SCF_SENS)) need = true;
+      if (lutDiff && lut_sensitive(B, s, runLut)) need = true;
       __syncthreads();
       if (need)
       {

@@ -48,7 +48,7 @@ static __global__ void k_enc_slice_inject(const EncBufs B, const Spec sp)
     if (sc.nSC > 0) { B.scIn[0] = want.st; if (sp.K) B.scLut[0] = want.lut; B.scDirty[0] = 1; }
   }
   sc.nDirty[0] = changed ? 1u : 0u; sc.firstDirty[0] = 0;
-  for (int r = 1; r < E2_ROUNDS; r++) { sc.done[r] = 0; sc.nDirty[r] = 0; sc.firstDirty[r] = 0; }
+  for (int r = 1; r < E2_MAXROUNDS; r++) { sc.done[r] = 0; sc.nDirty[r] = 0; sc.firstDirty[r] = 0; }
   B.msg->changed = changed ? 1u : 0u;
 }
 
