@@ -602,7 +602,6 @@ template <int W, int BA, int V, class SymT> struct EncCta
     // (2) verification; a LUT super-chunk whose decisions did not depend on the incoming table only takes the exact table
     AutoState st; Lut lut; enc_stream_incoming(B, W, st, lut);
     segsum_apply<K>(st, lut, pre);
-    uint64_t bytes = 0;
     uint32_t nd = 0, first = 0xFFFFFFFFu;
     for (uint32_t s = lo; s < hi; s++)
     {
@@ -611,13 +610,22 @@ template <int W, int BA, int V, class SymT> struct EncCta
       if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; if (lut_sensitive(B, s, lut)) bad = true; }
       B.scDirty[s] = bad ? 1 : 0;
       if (bad) { if (!nd) first = s; nd++; }
-      B.scBase[s] = bytes;                       // relative to the thread's first super-chunk until (3)
-      bytes += sc_bytes(B, s, lut);
       chunksum_apply(st, B.scSum[s]);
       if (K) lut_apply(lut, K, B.scAgg[s]);
     }
     if (nd) { atomicAdd(&sDirty, nd); atomicMin(&sFirst, first); }
-    // (3) token byte offsets: scan of the per-thread sums
+    __syncthreads();
+    const uint32_t nDirty = sDirty, firstDirty = sFirst;
+    if (t == 0) { sc.nDirty[round] = nDirty; sc.firstDirty[round] = firstDirty; }
+    if (nDirty != 0 && round < enc_rounds(W, K) - 1) return;          // another round follows: offsets are not needed yet
+    // (3) token byte offsets (scLut[s] now is the exact incoming table of every super-chunk): per-thread sums, scan
+    uint64_t bytes = 0;
+    for (uint32_t s = lo; s < hi; s++)
+    {
+      B.scBase[s] = bytes;                       // relative to the thread's first super-chunk
+      Lut li; if (K) li = B.scLut[s]; else lut_init(li, W);
+      bytes += sc_bytes(B, s, li);
+    }
     uint64_t incB = bytes;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(0xFFFFFFFFu, incB, d); if (lane >= d) incB += o; }
@@ -627,13 +635,10 @@ template <int W, int BA, int V, class SymT> struct EncCta
 #pragma unroll
     for (int w = 0; w < E2_T / 32; w++) { const uint64_t x = S.warpBytes[w]; if (w < warp) preB += x; totalBytes += x; }
     for (uint32_t s = lo; s < hi; s++) B.scBase[s] += preB;
-    const uint32_t nDirty = sDirty, firstDirty = sFirst;
-    if (t == 0) { sc.nDirty[round] = nDirty; sc.firstDirty[round] = firstDirty; }
     __syncthreads();
     AutoState fin; Lut finLut; enc_stream_incoming(B, W, fin, finLut);
     segsum_apply<K>(fin, finLut, total);
     if (nDirty == 0) { finish(B, fin, finLut, totalBytes, total.ntok); return; }
-    if (round < enc_rounds(W, K) - 1) return;
 
     // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
     // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA / one warp each)
@@ -673,7 +678,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
 };
 
 template <int W, int BA, int V, class SymT>
-__global__ void __launch_bounds__(E2_T, (V == V_LUT3 || V == V_LUT7) ? 4 : 1) k_enc_auto(const EncBufs B, int round)
+__global__ void __launch_bounds__(E2_T, ((V == V_LUT3 || V == V_LUT7) && W > 1) ? 4 : 1) k_enc_auto(const EncBufs B, int round)
 {
   using C = EncCta<W, BA, V, SymT>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
