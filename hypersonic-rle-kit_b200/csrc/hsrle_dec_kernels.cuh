@@ -394,7 +394,8 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
       for (int k = 0; k < DC_BATCH; k++)
       {
         const bool far = need[k] && code[k] >= EX_FARP;
-        farv[k] = __ldcg(D.farTab + (far ? (size_t)(x[k] / DEC_SCB) * DEC_SCB + (code[k] & 0x3FFFu) : (size_t)0));
+        // (the dummy address of the not-far case is a word that is always initialised: the scalars D1 wrote)
+        farv[k] = __ldcg(far ? D.farTab + ((size_t)(x[k] / DEC_SCB) * DEC_SCB + (code[k] & 0x3FFFu)) : reinterpret_cast<const uint32_t *>(D.sc));
       }
 #pragma unroll
       for (int k = 0; k < DC_BATCH; k++)
