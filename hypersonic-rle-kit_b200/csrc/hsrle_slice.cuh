@@ -79,7 +79,9 @@ HSRLE_HD SliceLink slice_link(const SliceMsg *all, int rank, int world)
 HSRLE_HD void slice_guess_state(const Spec &sp, int rank, uint32_t lo, SliceState &g)
 {
   g.st = enc_initial_state(); lut_init(g.lut, sp.W);
-  if (rank > 0) { g.st.cursor = lo; g.st.last = lo; }
+  // (W == 1 never reads or writes `cursor`: it must keep its initial value, or the difference to the true incoming
+  //  state would be carried through every super-chunk of the slice and each of them re-evaluated)
+  if (rank > 0) { g.st.cursor = sp.W == 1 ? 0u : lo; g.st.last = lo; }
 }
 // true incoming state of `rank` given everybody's current outgoing state
 HSRLE_HD void slice_incoming_state(const Spec &sp, const SliceMsg *all, int rank, SliceState &g)
