@@ -732,6 +732,12 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
   const uint32_t entry = D.scEntry[c];
   const bool hasTok = entry < POS_SPECIAL;
+  if (!hasTok && c != gridDim.x - 1 && (c % DX_GROUP) != DX_GROUP - 1)
+  { // no token starts in this SC (it lies inside a long literal) and nobody needs its prefix: publish the identity and go
+    if (t == 0) { decagg_store<K>(&aggBuf[c], decagg_identity<K>()); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
+    dec_emit_done(D, &S.flag);
+    return;
+  }
 
   // ---- the SC's tokens: chain marks, walk #1
   Agg mine = decagg_identity<K>();
