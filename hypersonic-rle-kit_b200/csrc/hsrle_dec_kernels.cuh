@@ -143,6 +143,7 @@ __device__ __forceinline__ uint32_t toklen(const TokWin &x, bool single, uint32_
 // farTab[c0 + q'].  D2 reads the table as codes and translates the few entries it needs; only the first DEC_WIN entries
 // of an SC (its windowed exit map, read by every call of D2) are also kept as absolute positions (winTab).
 constexpr int DM_T = 256;
+constexpr int DM_SCOUT = 8;                // true-chain tokens the scout of D1 follows at most
 constexpr uint32_t DEC_HB = 64;             // half mini-block: the unit one thread sweeps
 constexpr uint32_t DEC_LIN_BYTES = DEC_SCB + 48;
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
@@ -219,6 +220,37 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   const bool single = hs.single != 0;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   uint32_t *farRow = D.farTab + (size_t)c0;
+  // Scout: the first tokens of the TRUE chain can be followed from the stream start without any table as long as each
+  // of them jumps over whole SCs (incompressible input is one token with a literal of the whole input).  An SC such a
+  // token jumps over holds no token start: its tables only have to be safe for the speculative chains that land in it
+  // ("unparsable"), not computed.  The scout stops at the first ordinary token, i.e. after one parse on ordinary data.
+  {
+    __shared__ uint32_t sSkip;
+    if (t == 0)
+    {
+      uint32_t skip = 0, p = hs.first;
+      for (int i = 0; i < DM_SCOUT && p < c0; i++)
+      {
+        Tok tk; dec_parse(sp, single, D.in + p, (uint64_t)clen - p, tk);
+        if (!tk.valid) break;
+        if (tk.last) { skip = 1; break; }                             // the final token starts before this SC: nothing starts in it
+        const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
+        if (nx >= (uint64_t)c0 + DEC_SCB) { skip = 1; break; }        // starts before this SC, next token after it
+        if (tk.litLen < 4 * DEC_SCB) break;
+        p = (uint32_t)nx;
+      }
+      sSkip = skip;
+    }
+    __syncthreads();
+    if (sSkip)
+    {
+      const uint32_t bad2 = EX_BAD | (EX_BAD << 16);
+      uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
+      for (uint32_t q = t; q < DEC_SCB / 8; q += DM_T) dst[q] = make_uint4(bad2, bad2, bad2, bad2);
+      for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = POS_BAD;
+      return;
+    }
+  }
   uint16_t *const ex = S.ex();
   dec_load_sc_linear(S.data(), D.in, c0, clen);
   __syncthreads();
