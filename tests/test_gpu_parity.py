@@ -267,3 +267,32 @@ def test_workspace_contents_do_not_matter(hs, name):
         rd = res[8:].tolist()
         assert rd[0] == n and rd[1] == 0, (fill, rd)
         assert torch.equal(t_dec[:n], t_in)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle16_byte_packed", "rle32_3symlut_byte", "rle64_7symlut_sym"])
+def test_long_literals_at_stream_start(hs, name):
+    """D1's scout follows the true chain from the stream start while its tokens jump over whole super-chunks and gives the
+    super-chunks in between constant tables: streams that begin with 0..9 such tokens (literals of 64 KiB and more),
+    followed by ordinary tokens or by nothing, must decode exactly and the encoder must still match the oracle."""
+    codec = CODEC_BY_NAME[name]
+    rng = np.random.default_rng(2024)
+    W = codec.W
+    for nlong, tail in ((0, "dct"), (1, "dct"), (3, "dct"), (9, "dct"), (2, "none"), (1, "run"), (10, "short")):
+        parts = []
+        for k in range(nlong):
+            parts.append(rng.integers(0, 256, size=int(rng.integers(65536 + 20, 200000)), dtype=np.uint8))
+            parts.append(np.tile(rng.integers(0, 256, size=W, dtype=np.uint8), 40 + k))          # a run every codec emits
+        if tail == "dct":
+            parts.append(gen_dct(300000, seed=int(rng.integers(1, 1000))))
+        elif tail == "run":
+            parts.append(np.tile(rng.integers(0, 256, size=W, dtype=np.uint8), 50000))
+        elif tail == "short":
+            parts.append(gen_short_runs(100000, seed=3, W=W))
+        else:
+            parts.append(rng.integers(0, 256, size=70000, dtype=np.uint8))                          # final token with a long literal
+        data = np.concatenate(parts)
+        want = oracle_compress(codec, data)
+        got = gpu_enc(hs, codec, data)
+        assert np.array_equal(got, want), (name, nlong, tail)
+        r, dec = gpu_dec(hs, codec, want, len(data))
+        assert r == len(data) and np.array_equal(dec, data), (name, nlong, tail)
