@@ -158,6 +158,7 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.sc = cv.take<DecScalars>(1);
   D.flagAgg = cv.take<uint32_t>((size_t)D.nSC + 1); D.flagInc = cv.take<uint32_t>((size_t)D.nSC + 1);
   D.flagSeg = cv.take<uint32_t>((size_t)D.nSeg + 1); D.chainFlag = cv.take<uint32_t>((size_t)D.nSeg + 1);
+  D.scSkip = cv.take<uint32_t>((size_t)D.nSC + 1);
   D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);          // zeroed: 0 = "row not published yet"
   if (zeroBytes) *zeroBytes = cv.off;
   D.chainPos = cv.take<uint32_t>((size_t)D.nSeg + 1);

@@ -186,6 +186,7 @@ struct DecBufs
   uint16_t *scTab;          // [nSC][DEC_SCB]   per-position SC exit codes (D1 -> D2)
   uint32_t *farTab;         // [nSC][DEC_SCB]   absolute exit of the far-jumping token at that position (sparse)
   uint32_t *winTab;         // [nSC][DEC_WIN]   absolute SC exits of the window positions
+  uint32_t *scSkip;         // [nSC]  1: D1's scout found the SC jumped over by a true token (constant tables); cleared per call
   uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
   uint32_t *flagSeg, *chainFlag;   // [nSeg] "rows published" / "chain position published" (zeroed per call)
   uint32_t *chainPos;       // [nSeg] first position of the true chain at or after the start of the segment (or its end code)

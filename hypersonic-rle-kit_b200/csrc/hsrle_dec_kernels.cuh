@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
       uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
       for (uint32_t q = t; q < DEC_SCB / 8; q += DM_T) dst[q] = make_uint4(bad2, bad2, bad2, bad2);
       for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = POS_BAD;
+      if (t == 0) D.scSkip[c] = 1u;
       return;
     }
   }
@@ -397,6 +398,9 @@ static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
   for (uint32_t c = cFirst + w; c < min(cFirst + DEC_SEG, D.nSC); c += DC_T) D.scEntry[c] = POS_NONE;
   if (cFirst >= nSC) return;
   const uint32_t nHere = min(DEC_SEG, nSC - cFirst);
+  // a segment whose SCs were all jumped over by a true token (D1's scout) is never entered by the true chain: nobody will
+  // read its rows.  (The last segment still settles how the chain ended.)
+  if (__syncthreads_and(w >= nHere || D.scSkip[cFirst + w] != 0u) && g != nSegEff - 1) return;
   const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_SCB;
   const uint64_t segBytes = (uint64_t)DEC_SEG * DEC_SCB;
   // (1)
