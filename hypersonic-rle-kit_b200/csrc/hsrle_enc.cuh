@@ -39,7 +39,10 @@ constexpr int E2L_CH = 16;                // LUT codecs: records per lane -- one
 static_assert(E2L_CH * 32 == E2_SCR && E2L_CH % E2_CH == 0, "a warp covers one super-chunk");
 constexpr uint32_t SCF_SENS = 1;          // scFlags: a decision of the super-chunk depended on the incoming LUT
 constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
-constexpr int E2_ROUNDS = 3;              // grid-level rounds (the last one ends with the sequential repair)
+constexpr int E2_ROUNDS = 6;              // grid-level rounds (the last one ends with the sequential repair); rounds without dirt
+                                          // return at once.  3 rounds left 14-21 dirty super-chunks on short-run streams read with
+                                          // a wider symbol (rle24_byte_packed, rle32_sym: few tokens, the state passes through many
+                                          // super-chunks), and the sequential repair then re-ran 770-1,170 of them one by one (3-4 ms)
 constexpr int E2L1_ROUNDS = 24;           // ... for the 8-bit LUT codecs, whose table has long-range memory:
                                           // a changed table travels one super-chunk per round; rounds without dirt return at once
 constexpr int E2_MAXROUNDS = 24;

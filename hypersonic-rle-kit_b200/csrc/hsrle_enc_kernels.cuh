@@ -979,11 +979,17 @@ static __global__ void __launch_bounds__(256) k_enc_copy_big(const EncBufs B)
   }
   const uint32_t nBig = B.sc->nBig;
   constexpr uint32_t SUB = BIG_PIECE / 8;    // one sub-piece per warp
+  // the pieces of all huge literals are dealt round-robin over the CTAs as ONE sequence (a stream of 64-KiB..1-MiB literals
+  // has 4..64 pieces each: starting every literal at CTA 0 left most of the grid idle -- 88 MB in such literals took
+  // 1.3 ms); rot = pieces of the literals before this one, modulo the grid
+  uint32_t rot = 0;
   for (uint32_t i = 0; i < nBig; i++)
   {
     const CopyDesc cd = B.bigList[i];
     const uint32_t nPieces = (cd.len + BIG_PIECE - 1) / BIG_PIECE;
-    for (uint32_t pc = blockIdx.x; pc < nPieces; pc += gridDim.x)
+    const uint32_t first = (blockIdx.x + gridDim.x - rot) % gridDim.x;
+    rot = (rot + nPieces) % gridDim.x;
+    for (uint32_t pc = first; pc < nPieces; pc += gridDim.x)
     {
       const uint32_t off = pc * BIG_PIECE + warp * SUB;
       if (off >= cd.len) continue;
