@@ -296,3 +296,29 @@ def test_long_literals_at_stream_start(hs, name):
         assert np.array_equal(got, want), (name, nlong, tail)
         r, dec = gpu_dec(hs, codec, want, len(data))
         assert r == len(data) and np.array_equal(dec, data), (name, nlong, tail)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle24_byte_packed", "rle32_sym", "rle48_byte", "rle64_3symlut_sym"])
+def test_many_huge_literals_in_mid_stream(hs, name):
+    """A stream that is mostly literal bytes with a token every 2 KiB .. 1 MiB (what a wide-symbol codec makes of a
+    byte-run stream): the encoder's grid-wide literal copy deals the 16-KiB pieces of all huge literals round-robin over
+    the CTAs (hundreds of literals: the rotation wraps around the grid), and the decoder's segment composition (D2) keeps
+    taking batched hops while many speculative chains enter super-chunk after super-chunk beyond the window."""
+    codec = CODEC_BY_NAME[name]
+    rng = np.random.default_rng(77)
+    W = codec.W
+    parts = []
+    total = 0
+    while total < 40 << 20:
+        ll = int(2 ** rng.uniform(11, 20))
+        parts.append(rng.integers(0, 256, size=ll, dtype=np.uint8))
+        rl = int(rng.integers(12, 60))
+        parts.append(np.tile(rng.integers(0, 256, size=W, dtype=np.uint8), rl))
+        total += ll + rl * W
+    parts.append(gen_short_runs(200000, seed=5, W=1))
+    data = np.concatenate(parts)
+    want = oracle_compress(codec, data)
+    got = gpu_enc(hs, codec, data)
+    assert np.array_equal(got, want), name
+    r, dec = gpu_dec(hs, codec, want, len(data))
+    assert r == len(data) and np.array_equal(dec, data), name
