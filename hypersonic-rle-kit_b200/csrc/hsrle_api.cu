@@ -218,7 +218,10 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
   const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
-  for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+  // late rounds see a few dozen dirty super-chunks at most (usually none: they return at once): one CTA per SM keeps
+  // the empty launches cheap (the kernel strides over the super-chunks with whatever grid it gets)
+  const int lateGrid = std::min(autoGrid, sms);
+  for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, r < 3 ? autoGrid : lateGrid, E2_T, k->autoSmem, st, B, r);
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
