@@ -32,7 +32,11 @@ static std::vector<TimedLaunch> g_timed;
 #define HSRLE_LAUNCH_NAMED(name, kern, grid, block, smem, stream, ...)     \
   do {                                                                     \
     TimedLaunch tl_{ name, nullptr, nullptr };                             \
-    if (g_timing) { cudaEventCreate(&tl_.a); cudaEventCreate(&tl_.b); cudaEventRecord(tl_.a, (stream)); } \
+    if (g_timing && cudaEventCreate(&tl_.a) == cudaSuccess)                \
+    {                                                                      \
+      if (cudaEventCreate(&tl_.b) != cudaSuccess) { cudaEventDestroy(tl_.a); tl_.a = nullptr; } \
+      else cudaEventRecord(tl_.a, (stream));                               \
+    }                                                                      \
     kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
     if (tl_.a) { cudaEventRecord(tl_.b, (stream)); std::lock_guard<std::mutex> lk_(g_timedMu); g_timed.push_back(tl_); } \
     g_launches.fetch_add(1, std::memory_order_relaxed);                    \
@@ -46,16 +50,25 @@ static bool cuda_ok(cudaError_t e, const char *what)
   return false;
 }
 
-static int g_numSM = 0;
+// per-device caches: cudaFuncSetAttribute and the SM count belong to the CURRENT device, and one process may use several
+constexpr int MAX_DEV = 64;
+static int current_dev()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) dev = 0;
+  return dev;
+}
+static std::atomic<int> g_numSM[MAX_DEV];
 static int num_sms()
 {
-  if (g_numSM == 0)
+  const int dev = current_dev();
+  int n = g_numSM[dev].load(std::memory_order_relaxed);
+  if (n == 0)
   {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_numSM = n;
-    else g_numSM = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_numSM[dev].store(n, std::memory_order_relaxed);
   }
-  return g_numSM;
+  return n;
 }
 
 // ================================================================================================
@@ -184,11 +197,12 @@ static bool spec_from_codec(int codec, Spec &sp)
 }
 
 static std::mutex g_attrMu;
-static bool g_attrDone[48];
+static bool g_attrDone[MAX_DEV][48];
 static bool enc_prepare(int codec, const EncKernels *k)
 {
+  const int dev = current_dev();
   std::lock_guard<std::mutex> lk(g_attrMu);
-  if (g_attrDone[codec]) return true;
+  if (g_attrDone[dev][codec]) return true;
   // the bandwidth kernels ask for the same (maximum) shared-memory carve-out: CTAs of kernels with different carve-outs
   // cannot share an SM, and the calls of several streams are meant to overlap.  Not the automaton: its register-capped
   // LUT variants keep spilled table entries in L1 (measured: +10 % time with the small L1)
@@ -197,7 +211,7 @@ static bool enc_prepare(int codec, const EncKernels *k)
   cudaFuncSetAttribute((const void *)k_enc_copy_big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->autom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->autoSmem), "attr auto")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
-  g_attrDone[codec] = true;
+  g_attrDone[dev][codec] = true;
   return true;
 }
 
@@ -300,24 +314,25 @@ static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
 }
 
 static std::mutex g_dattrMu;
-static bool g_dattrDone[48];
-static bool g_composeAttr = false;
+static bool g_dattrDone[MAX_DEV][48];
+static bool g_composeAttr[MAX_DEV];
 static bool dec_prepare(int codec, const DecKernels *k)
 {
+  const int dev = current_dev();
   std::lock_guard<std::mutex> lk(g_dattrMu);
-  if (!g_composeAttr)
+  if (!g_composeAttr[dev])
   {
     if (!cuda_ok(cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem)), "attr chain")) return false;
-    g_composeAttr = true;
+    g_composeAttr[dev] = true;
   }
-  if (g_dattrDone[codec]) return true;
+  if (g_dattrDone[dev][codec]) return true;
   cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute((const void *)k->big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
-  g_dattrDone[codec] = true;
+  g_dattrDone[dev][codec] = true;
   return true;
 }
 
@@ -402,7 +417,6 @@ struct ContextLease
   }
   ~ContextLease() { std::lock_guard<std::mutex> lk(g_poolMu); g_pool.push_back(c); }
 };
-static void set_func_attrs() {}
 
 static uint32_t run_sync(Context &C, bool compress, int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize)
 {
@@ -493,13 +507,11 @@ size_t hsrle_decompress_workspace_size(int codec, uint32_t inSize, uint32_t outS
 int hsrle_compress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
                                 void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream)
 {
-  set_func_attrs();
   return enc_enqueue(codec, dIn, inSize, dOut, outSize, dWorkspace, workspaceSize, dResult, (cudaStream_t)cudaStream);
 }
 int hsrle_decompress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
                                   void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream)
 {
-  set_func_attrs();
   return dec_enqueue(codec, dIn, inSize, dOut, outSize, dWorkspace, workspaceSize, dResult, (cudaStream_t)cudaStream);
 }
 
@@ -564,6 +576,7 @@ int hsrle_slice_compress_phase(const hsrle_slice_job *job, int phase, void *cuda
 
 void hsrle_timing_begin(void)
 {
+  std::lock_guard<std::mutex> lk(g_timedMu);
   for (auto &t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   g_timed.clear(); g_timing = true;
 }
@@ -574,6 +587,7 @@ int hsrle_timing_end(char *buf, int bufSize)
   g_timing = false;
   cudaDeviceSynchronize();
   std::map<std::string, std::pair<int, double>> acc;
+  std::lock_guard<std::mutex> lk(g_timedMu);
   for (auto &t : g_timed)
   {
     float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);

@@ -267,3 +267,74 @@ def gen_run_mixed(n, seed=11, max_run_log2=20, max_lit_log2=16):
         parts.append(rng.integers(0, 256, size=ll, dtype=np.uint8))
         total += rl + ll
     return np.concatenate(parts)[:n].copy()
+
+
+# --------------------------------------------------------------------------- configs[3]: multi-GiB run-mixed stream
+RM_PIECE = 64 << 20          # the stream is defined piece by piece: any rank can materialise any piece on its own
+
+
+def _rm_boundary_symbol(k, seed):
+    """8-byte run symbol that straddles the boundary between pieces k-1 and k (also frame and slice boundaries)."""
+    r = np.random.default_rng([seed, 0xB0DE, k])
+    return r.integers(0, 256, size=8, dtype=np.uint8)
+
+
+def run_mixed_piece_table(piece, seed=0xC3, piece_bytes=RM_PIECE):
+    """Segment table of one piece: alternating runs (length log-uniform 2..2^20, symbol width 1 or 8)
+    and random literals (log-uniform 1..2^16).  The first and the last segment are runs whose symbols are shared with
+    the neighbouring pieces, so a run straddles every piece boundary by construction.
+    Returns (lengths int64[S], is_run bool[S], sym uint8[S, 8])."""
+    r = np.random.default_rng([seed, piece])
+    lens, isrun, syms = [], [], []
+    first = int(r.integers(16, 4096))
+    lens.append(first); isrun.append(True); syms.append(_rm_boundary_symbol(piece, seed))
+    total = first
+    tail = int(r.integers(16, 4096))
+    while True:
+        ll = int(2 ** r.uniform(0, 16))
+        rl = int(2 ** r.uniform(1, 20))
+        if total + ll + rl + tail >= piece_bytes:
+            break
+        lens.append(ll); isrun.append(False); syms.append(np.zeros(8, dtype=np.uint8))
+        s = r.integers(0, 256, size=8, dtype=np.uint8)
+        if r.random() < 0.5:
+            s[:] = s[0]                                   # symbol width 1
+        lens.append(rl); isrun.append(True); syms.append(s)
+        total += ll + rl
+    rest = piece_bytes - total
+    ll = max(1, rest - tail)
+    lens.append(ll); isrun.append(False); syms.append(np.zeros(8, dtype=np.uint8))
+    lens.append(rest - ll); isrun.append(True); syms.append(_rm_boundary_symbol(piece + 1, seed))
+    if lens[-1] == 0:
+        lens.pop(); isrun.pop(); syms.pop()
+    assert sum(lens) == piece_bytes
+    return np.array(lens, dtype=np.int64), np.array(isrun, dtype=bool), np.stack(syms)
+
+
+def gen_run_mixed_pieces(first_piece, n_pieces, device, seed=0xC3, piece_bytes=RM_PIECE):
+    """Bytes [first_piece * piece_bytes, (first_piece + n_pieces) * piece_bytes) of the configs[3] stream as a torch
+    uint8 tensor on `device` (segment tables from numpy, expansion with torch ops; literal bytes are a counter-based
+    hash of the absolute position, run bytes the segment's 8-byte symbol at phase position % 8)."""
+    import torch
+    out = torch.empty(n_pieces * piece_bytes, dtype=torch.uint8, device=device)
+    for i in range(n_pieces):
+        piece = first_piece + i
+        lens, isrun, syms = run_mixed_piece_table(piece, seed, piece_bytes)
+        t_len = torch.from_numpy(lens).to(device)
+        seg = torch.repeat_interleave(torch.arange(len(lens), dtype=torch.int16, device=device), t_len)
+        pos = torch.arange(piece_bytes, dtype=torch.int64, device=device) + piece * piece_bytes
+        x = pos * -7046029254386353131 + (seed * 1000003 + 12345)      # 0x9E3779B97F4A7C15 as int64; wraps
+        x ^= x >> 29
+        x *= -4658895280553007687                                      # 0xBF58476D1CE4E5B9 as int64
+        x ^= x >> 32
+        lit = (x & 0xFF).to(torch.uint8)
+        del x
+        seg_l = seg.to(torch.int64)
+        del seg
+        t_sym = torch.from_numpy(syms.reshape(-1)).to(device)
+        run = t_sym[seg_l * 8 + (pos & 7)]
+        t_isrun = torch.from_numpy(isrun).to(device)[seg_l]
+        del seg_l, pos
+        out[i * piece_bytes:(i + 1) * piece_bytes] = torch.where(t_isrun, run, lit)
+        del run, lit, t_isrun
+    return out

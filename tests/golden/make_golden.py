@@ -83,6 +83,23 @@ def main():
     with open(os.path.join(HERE, "golden_hashes.json"), "w") as f:
         json.dump(hashes, f, indent=1, sort_keys=True)
     print("wrote", len(blob), "arrays and", len(hashes), "hash sets")
+    write_full_size()
+
+
+FULL_N = 88473600      # BASELINE configs[0,1]: the video-frame.raw shape (README.md:25)
+
+
+def write_full_size():
+    """Reference stream length + sha256 of every codec on the full 88,473,600-byte DCT stream (the bench input):
+    tests/golden/golden_hashes_88m.json, asserted by tests/test_gpu_parity.py and by bench.py before it times."""
+    v = gen_dct(FULL_N)
+    out = {"input": "gen_dct(88473600) (SURVEY App. E.1)", "input_sha256": hashlib.sha256(v.tobytes()).hexdigest(), "n": FULL_N, "streams": {}}
+    for c in CODECS:
+        s = ref_compress(c, v)
+        out["streams"][c.name] = {"len": int(len(s)), "sha256": hashlib.sha256(s.tobytes()).hexdigest()}
+    with open(os.path.join(HERE, "golden_hashes_88m.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("wrote full-size hashes for", len(out["streams"]), "codecs")
 
 
 if __name__ == "__main__":

@@ -1,8 +1,8 @@
 // hsrle_dec_v1.cuh -- first-generation decoder stages (boundary maps -> hierarchical resolution -> token
 // walk -> per-vector expansion).  Kept while the single-pass decoder replaces it stage by stage.
 #pragma once
-#include "hsrle_core.cuh"
-#include "hsrle_enc.cuh"   // ST_* status codes
+#include "../../hypersonic-rle-kit_b200/csrc/hsrle_core.cuh"
+#include "../../hypersonic-rle-kit_b200/csrc/hsrle_enc.cuh"   // ST_* status codes
 
 namespace hsrle {
 

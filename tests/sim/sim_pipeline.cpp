@@ -4,7 +4,7 @@
 // and sequential repair -> emit; boundary maps -> resolution -> walk -> expansion) so they can be compared
 // with the oracle in a container without a GPU.  Never part of the product library: the product has no CPU path.
 #include "../../hypersonic-rle-kit_b200/csrc/hsrle_enc.cuh"
-#include "../../hypersonic-rle-kit_b200/csrc/hsrle_dec_v1.cuh"
+#include "hsrle_dec_v1.cuh"
 #include <cstdio>
 #include <cstring>
 #include <vector>

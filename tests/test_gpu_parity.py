@@ -174,67 +174,156 @@ def test_device_resident_and_async_paths(hs):
         assert np.array_equal(t_dec[: len(data)].cpu().numpy(), data)
 
 
-@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle64_byte_packed", "rle24_3symlut_sym"])
-def test_full_size_88mb_roundtrip(hs, name):
-    """BASELINE configs[0,1] size: 88,473,600-byte DCT stream; encoder parity against the oracle and
-    encode -> decode round trip on the device."""
+@pytest.fixture(scope="module")
+def full88():
+    """The bench input (BASELINE configs[0,1]): 88,473,600-byte DCT stream, resident on the device once per module."""
+    import json
+    import os
     import torch
-    codec = CODEC_BY_NAME[name]
     n = 88473600
     data = gen_dct(n)
-    want = oracle_compress(codec, data)
-    dev = torch.device("cuda:0")
-    t_in = torch.from_numpy(data).to(dev)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_hashes_88m.json")) as f:
+        gold = json.load(f)
+    assert gold["n"] == n and hashlib.sha256(data.tobytes()).hexdigest() == gold["input_sha256"]
+    return data, torch.from_numpy(data).to(torch.device("cuda:0")), gold["streams"]
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_full_size_88mb_all_codecs(hs, codec, full88):
+    """BASELINE configs[0,1] at full size, every codec: the GPU stream is byte-identical to the compiled reference's
+    (length + sha256 from tests/golden/golden_hashes_88m.json, made by make_golden.py from oracle/_ref) and decodes back."""
+    import torch
+    data, t_in, gold = full88
+    n = len(data)
+    dev = t_in.device
     t_out = torch.empty(out_capacity(n), dtype=torch.uint8, device=dev)
-    r = hs.compress_device(name, t_in, t_out)
-    assert r == len(want), (r, len(want), hs.last_error())
-    assert torch.equal(t_out[:r].cpu(), torch.from_numpy(want))
+    r = hs.compress_device(codec.name, t_in, t_out)
+    assert r == gold[codec.name]["len"], (codec.name, r, gold[codec.name]["len"], hs.last_error())
+    assert hashlib.sha256(t_out[:r].cpu().numpy().tobytes()).hexdigest() == gold[codec.name]["sha256"], codec.name
     t_dec = torch.empty(n + 128, dtype=torch.uint8, device=dev)
-    rd = hs.decompress_device(name, t_out, r, t_dec, n)
-    assert rd == n
+    rd = hs.decompress_device(codec.name, t_out, r, t_dec, n)
+    assert rd == n, (codec.name, hs.last_error())
     assert torch.equal(t_dec[:n], t_in)
 
 
-@pytest.mark.parametrize("name", ["rle8_multi", "rle64_byte_packed", "rle32_3symlut_byte"])
-@pytest.mark.parametrize("kind", ["single_symbol", "random", "alternating", "run_mixed"])
-def test_one_gib_frame_properties(hs, name, kind):
-    """BASELINE configs[4] at the frame size (2^30 bytes, the largest input rle_compress_bounds accepts,
-    src/rle8_extreme_cpu.c:24-25): the oracle is too slow here, so the checks are size-independent properties --
-    header fields, the stream-size bounds the format implies, and the encode -> decode round trip."""
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle64_byte_packed", "rle24_3symlut_sym"])
+def test_full_size_88mb_vs_oracle(hs, name, full88):
+    """Same size against the oracle port (the second, independent checker)."""
     import torch
-    dev = torch.device("cuda:0")
-    n = 1 << 30
+    codec = CODEC_BY_NAME[name]
+    data, t_in, _ = full88
+    n = len(data)
+    want = oracle_compress(codec, data)
+    t_out = torch.empty(out_capacity(n), dtype=torch.uint8, device=t_in.device)
+    r = hs.compress_device(name, t_in, t_out)
+    assert r == len(want), (r, len(want), hs.last_error())
+    assert torch.equal(t_out[:r].cpu(), torch.from_numpy(want))
+
+
+def _frame_input(kind, n, dev):
+    import torch
     g = torch.Generator(device=dev); g.manual_seed(77)
     if kind == "single_symbol":
-        t_in = torch.full((n,), 0x5A, dtype=torch.uint8, device=dev)
-    elif kind == "random":
-        t_in = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
-    elif kind == "alternating":
-        t_in = torch.arange(n, dtype=torch.int32, device=dev).bitwise_and_(1).to(torch.uint8)     # 1-byte runs: no candidates for W = 1
-    else:
-        # runs of 1 .. 4096 equal bytes: segment id = cumulative sum of "a new run starts here" flags
-        starts = torch.rand(n, device=dev, generator=g) < (1.0 / 37.0)
-        seg = torch.cumsum(starts.to(torch.int32), 0)
-        del starts
-        t_in = (seg.to(torch.int64) * 2654435761 % 251).to(torch.uint8)
-        del seg
+        return torch.full((n,), 0x5A, dtype=torch.uint8, device=dev)
+    if kind == "random":
+        return torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    if kind == "alternating":
+        return torch.arange(n, dtype=torch.int32, device=dev).bitwise_and_(1).to(torch.uint8)     # 1-byte runs: no candidates for W = 1
+    # runs of 1 .. 4096 equal bytes: segment id = cumulative sum of "a new run starts here" flags
+    starts = torch.rand(n, device=dev, generator=g) < (1.0 / 37.0)
+    seg = torch.cumsum(starts.to(torch.int32), 0)
+    del starts
+    t_in = (seg.to(torch.int64) * 2654435761 % 251).to(torch.uint8)
+    del seg
+    return t_in
+
+
+def _check_frame(hs, name, t_in, kind=None):
+    """Encode one frame on the device, compare the stream with the compiled reference's (oracle/_ref, ~1 s per GiB on the
+    host), check the header, decode back.  Returns the stream length."""
+    import torch
     codec = CODEC_BY_NAME[name]
+    n = t_in.numel()
+    dev = t_in.device
     cap = n + n // 256 + 512
     t_out = torch.empty(cap, dtype=torch.uint8, device=dev)
     r = hs.compress_device(name, t_in, t_out)
     assert r > 0, hs.last_error()
-    hdr = t_out[:9].cpu().numpy()
-    assert int.from_bytes(hdr[0:4].tobytes(), "little") == n and int.from_bytes(hdr[4:8].tobytes(), "little") == r
+    got = t_out[:r].cpu().numpy()
+    assert int.from_bytes(got[0:4].tobytes(), "little") == n and int.from_bytes(got[4:8].tobytes(), "little") == r
     if codec.W == 1 and codec.variant in (0, 1):
-        assert hdr[8] == 0                                   # multi mode
+        assert got[8] == 0                                   # multi mode
     if kind == "single_symbol":
         assert r < 64                                        # header + one token + terminator
     if kind == "random":
         assert n <= r <= n + n // 256 + 64                   # (almost) one literal; a few accidental short runs at most
+    if ref_lib() is not None:
+        want = ref_compress(codec, t_in.cpu().numpy())
+        assert len(want) == r and np.array_equal(got, want), (name, kind, r, len(want))
+        del want
+    del got
     t_dec = torch.empty(n + 128, dtype=torch.uint8, device=dev)
     rd = hs.decompress_device(name, t_out, r, t_dec, n)
     assert rd == n, hs.last_error()
     assert torch.equal(t_dec[:n], t_in)
+    return r
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle64_byte_packed", "rle32_3symlut_byte"])
+@pytest.mark.parametrize("kind", ["single_symbol", "random", "alternating", "run_mixed"])
+def test_one_gib_frame_vs_reference(hs, name, kind):
+    """BASELINE configs[4] at the frame size (2^30 bytes, the largest input rle_compress_bounds accepts,
+    src/rle8_extreme_cpu.c:24-25): the stream must equal the compiled reference's byte for byte (oracle/_ref travels
+    to the GPU box), plus header fields, the size bounds the format implies and the round trip."""
+    import torch
+    dev = torch.device("cuda:0")
+    _check_frame(hs, name, _frame_input(kind, 1 << 30, dev), kind)
+
+
+@pytest.mark.parametrize("name", ["rle8_multi", "rle64_byte"])
+def test_four_gib_single_symbol_as_frames(hs, name):
+    """BASELINE configs[4] "single-symbol 4 GiB (one run)": above 2^30 bytes rle_compress_bounds returns 0
+    (src/rle8_extreme_cpu.c:22-28) and the header fields are u32, so a caller of the u32 API cuts the input into frames
+    (hsrle_b200.sliced.frame_bounds); every frame is a complete reference-identical stream."""
+    import torch
+    from hsrle_b200.sliced import frame_bounds
+    dev = torch.device("cuda:0")
+    total = 4 << 30
+    t_in = torch.full((total,), 0x5A, dtype=torch.uint8, device=dev)
+    frames = frame_bounds(total)
+    assert len(frames) == 4 and all(b - a == 1 << 30 for a, b in frames)
+    sizes = [_check_frame(hs, name, t_in[a:b], "single_symbol") for a, b in frames]
+    assert len(set(sizes)) == 1
+
+
+@pytest.mark.parametrize("name", ["rle8_packed_multi", "rle48_byte", "rle16_7symlut_sym"])
+@pytest.mark.parametrize("n", [(1 << 30) - 1, 1 << 30])
+def test_frame_size_limits_vs_reference(hs, name, n):
+    """The API ceiling itself: frames of exactly 2^30 and 2^30 - 1 bytes (run-mixed content, the last byte inside a run)."""
+    import torch
+    dev = torch.device("cuda:0")
+    t_in = _frame_input("run_mixed", 1 << 30, dev)[:n].clone()
+    _check_frame(hs, name, t_in, "run_mixed")
+
+
+def test_two_devices_in_one_process(hs):
+    """Kernel attributes (dynamic shared memory) are per device: encode + decode on cuda:0, then on cuda:1."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    data = gen_dct(1 << 20, seed=9)
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            for name in ("rle8_multi", "rle32_3symlut_byte"):
+                want = oracle_compress(CODEC_BY_NAME[name], data)
+                t_in = torch.from_numpy(data).to(dev)
+                t_out = torch.empty(out_capacity(len(data)), dtype=torch.uint8, device=dev)
+                r = hs.compress_device(name, t_in, t_out)
+                assert r == len(want) and np.array_equal(t_out[:r].cpu().numpy(), want), (d, name, hs.last_error())
+                t_dec = torch.empty(len(data) + 128, dtype=torch.uint8, device=dev)
+                assert hs.decompress_device(name, t_out, r, t_dec, len(data)) == len(data), (d, name, hs.last_error())
+                assert torch.equal(t_dec[: len(data)], t_in)
 
 
 @pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle16_7symlut_byte", "rle48_3symlut_sym", "rle64_byte"])
@@ -322,3 +411,38 @@ def test_many_huge_literals_in_mid_stream(hs, name):
     assert np.array_equal(got, want), name
     r, dec = gpu_dec(hs, codec, want, len(data))
     assert r == len(data) and np.array_equal(dec, data), name
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_packed_multi", "rle8_3symlut", "rle16_sym_packed", "rle24_7symlut_byte", "rle32_byte",
+                                  "rle48_3symlut_sym", "rle64_byte_packed"])
+def test_corrupt_token_streams_fail_safely(hs, name):
+    """The reference trusts the stream (corrupt input = undefined behaviour); the library must not: bit-flipped
+    and truncated token bodies behind a VALID header either decode to exactly `uncompressedLength` bytes or return 0 -- within
+    the test timeout (no spin-wait may hang on a broken chain) and without writing a byte past the declared output size."""
+    import torch
+    dev = torch.device("cuda:0")
+    codec = CODEC_BY_NAME[name]
+    rng = np.random.default_rng(4242)
+    for data in (gen_dct(300000, seed=31), gen_fuzz(rng, 70000, long_every=13), gen_short_runs(120000, seed=33, W=codec.W)):
+        n = len(data)
+        good = gpu_enc(hs, codec, data)
+        variants = []
+        for k in range(10):
+            bad = good.copy()
+            nflip = int(rng.integers(1, 6))
+            pos = rng.integers(codec.hdr + 1, len(bad), size=nflip)
+            bad[pos] ^= (1 << rng.integers(0, 8, size=nflip)).astype(np.uint8)
+            variants.append(bad)
+        cut = good[: max(codec.hdr + 2, len(good) - int(rng.integers(1, 400)))].copy()
+        cut[4:8] = np.frombuffer(np.uint32(len(cut)).tobytes(), dtype=np.uint8)       # truncated, header made consistent
+        variants.append(cut)
+        junk = good.copy()
+        junk[codec.hdr + 1:] = rng.integers(0, 256, size=len(junk) - codec.hdr - 1, dtype=np.uint8)
+        variants.append(junk)
+        for bad in variants:
+            t_s = torch.from_numpy(bad).to(dev)
+            t_dec = torch.full((n + 256,), 0xEE, dtype=torch.uint8, device=dev)
+            r = hs.decompress_device(name, t_s, len(bad), t_dec, n)
+            assert r in (0, n), (name, r)
+            assert bool((t_dec[n:] == 0xEE).all()), name + ": wrote past the declared output size"
