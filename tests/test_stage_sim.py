@@ -18,7 +18,8 @@ _u8p = ctypes.POINTER(ctypes.c_uint8)
 def sim():
     so = os.path.join(SIM_DIR, "libsim.so")
     src = os.path.join(SIM_DIR, "sim_pipeline.cpp")
-    hdrs = [os.path.join(ROOT, "hypersonic-rle-kit_b200", "csrc", h) for h in ("hsrle_core.cuh", "hsrle_enc.cuh", "hsrle_dec_v1.cuh")]
+    hdrs = [os.path.join(ROOT, "hypersonic-rle-kit_b200", "csrc", h) for h in ("hsrle_core.cuh", "hsrle_enc.cuh")] + \
+           [os.path.join(SIM_DIR, "hsrle_dec_v1.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(so) or os.path.getmtime(so) < newest:
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", so, src], check=True)
