@@ -33,7 +33,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-os.environ.setdefault("NCCL_DEBUG", "WARN")     # NCCL's version banner goes to stdout; the contract is ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / logs must not reach stdout: the contract is ONE JSON line
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "hypersonic-rle-kit_b200"))
 
