@@ -118,6 +118,13 @@ static uint32_t enc_scan_steps(uint32_t nVec)
   return best;
 }
 
+// grid of the verify / repair kernel: the master CTA plus helpers for rounds with many dirty super-chunks.  Few super-chunks
+// (small inputs) never have such rounds: the master alone.
+static int enc_fix_grid(const EncBufs &B, int sms)
+{
+  return B.maxSC <= 4 * FIX_SOLO ? 1 : std::min<int>(sms, 1 + (int)(B.maxSC / 64));
+}
+
 static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t *zeroBytes)
 {
   Carver cv{ (uint8_t *)ws, 0 };
@@ -210,6 +217,7 @@ static bool enc_prepare(int codec, const EncKernels *k)
   cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute((const void *)k_enc_copy_big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->autom, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->autoSmem), "attr auto")) return false;
+  if (!cuda_ok(cudaFuncSetAttribute((const void *)k->fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->fixSmem), "attr fix")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
   g_attrDone[dev][codec] = true;
   return true;
@@ -232,10 +240,8 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
   const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
-  // late rounds see a few dozen dirty super-chunks at most (usually none: they return at once): one CTA per SM keeps
-  // the empty launches cheap (the kernel strides over the super-chunks with whatever grid it gets)
-  const int lateGrid = std::min(autoGrid, sms);
-  for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, r < 3 ? autoGrid : lateGrid, E2_T, k->autoSmem, st, B, r);
+  HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B);
+  HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K));
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
@@ -295,11 +301,12 @@ static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
       break;
     case 1:   // boundary-run fix-up, automaton from the assumed incoming state
       HSRLE_LAUNCH(k_enc_slice_link, 1, 32, 0, st, B, sp);
-      for (int r = 0; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B);
+      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K));
       break;
     case 2:   // true incoming state, repair rounds
       HSRLE_LAUNCH(k_enc_slice_inject, 1, 32, 0, st, B, sp);
-      for (int r = 1; r < enc_rounds(sp.W, sp.K); r++) HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B, r);
+      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, 1, FIX_T, k->fixSmem, st, B, 1, enc_rounds(sp.W, sp.K));
       break;
     case 3:   // tokens
       HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);

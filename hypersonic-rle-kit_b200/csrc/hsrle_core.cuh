@@ -255,6 +255,105 @@ HSRLE_HD LutAgg lutagg_combine(const LutAgg &older, const LutAgg &newer, int K)
 }
 
 // ------------------------------------------------------------------------------------------------
+// W == 1: table entries are single bytes, so the whole K-entry table is ONE 64-bit word (entry i in byte i) and every
+// table operation is a handful of integer instructions instead of 7-way unrolled 64-bit select chains.  Same semantics
+// as Lut / LutAgg above (the kernels pick the representation per symbol width; global-memory records keep the generic
+// layout and are converted at the boundaries).
+struct LutB { uint64_t v; };
+struct LutAggB { uint32_t m; uint32_t pad; uint64_t v; };
+HSRLE_HD uint64_t lutb_mask(int cnt) { return cnt >= 8 ? ~0ull : ((1ull << (8 * cnt)) - 1ull); }
+HSRLE_HD int lutb_ctz(uint64_t z)
+{
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)z) - 1;
+#else
+  return __builtin_ctzll(z);
+#endif
+}
+// index of byte `sym` among the low `cnt` bytes of v (cnt if absent); the lowest zero byte of the xor is found exactly
+HSRLE_HD int lutb_find(uint64_t v, int cnt, uint32_t sym)
+{
+  const uint64_t x = v ^ (0x0101010101010101ull * (uint64_t)(sym & 0xFFu));
+  const uint64_t z = (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull & lutb_mask(cnt);
+  return z ? (lutb_ctz(z) >> 3) : cnt;
+}
+// bytes below `from` move up by one, bytes above it stay, `sym` becomes byte 0
+HSRLE_HD uint64_t lutb_front(uint64_t v, int from, uint32_t sym)
+{
+  const uint64_t low = lutb_mask(from), high = ~lutb_mask(from + 1);
+  return ((v & low) << 8) | (v & high) | (uint64_t)(sym & 0xFFu);
+}
+HSRLE_HD void lut_init(LutB &l, int) { l.v = 0x00FE807E01FF7F00ull; }      // bytes 00 7F FF 01 7E 80 FE (src/rleX_Xsl.h:279-287)
+HSRLE_HD bool lut_equal(const LutB &a, const LutB &b, int K) { return ((a.v ^ b.v) & lutb_mask(K)) == 0; }
+HSRLE_HD int lut_find(const LutB &l, int K, uint64_t sym) { return lutb_find(l.v, K, (uint32_t)sym); }
+HSRLE_HD void lut_touch(LutB &l, int K, int idx, uint64_t sym) { l.v = lutb_front(l.v, idx == K ? K - 1 : idx, (uint32_t)sym) & lutb_mask(K); }
+HSRLE_HD uint64_t lut_front(const LutB &l) { return l.v & 0xFFu; }
+HSRLE_HD uint64_t lut_front(const Lut &l) { return l.s[0]; }
+HSRLE_HD void lutagg_push(LutAggB &a, int K, uint64_t sym)
+{
+  int idx = lutb_find(a.v, (int)a.m, (uint32_t)sym);
+  if (idx == (int)a.m) { if ((int)a.m < K) a.m++; else idx = K - 1; }
+  a.v = lutb_front(a.v, idx, (uint32_t)sym) & lutb_mask(K);
+}
+HSRLE_HD void lut_apply(LutB &l, int K, const LutAggB &a)
+{
+  if (a.m == 0) return;
+  uint64_t r = a.v & lutb_mask((int)a.m);
+  int k = (int)a.m;
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
+  {
+    if (i < K)
+    {
+      const uint32_t b = (uint32_t)(l.v >> (8 * i)) & 0xFFu;
+      if (k < K && lutb_find(a.v, (int)a.m, b) == (int)a.m) { r |= (uint64_t)b << (8 * k); k++; }
+    }
+  }
+  l.v = r;
+}
+HSRLE_HD LutAggB lutagg_combine(const LutAggB &older, const LutAggB &newer, int K)
+{
+  LutAggB r; r.pad = 0; r.m = newer.m; r.v = newer.v & lutb_mask((int)newer.m);
+  HSRLE_UNROLL
+  for (int i = 0; i < 7; i++)
+  {
+    if (i < K && i < (int)older.m)
+    {
+      const uint32_t b = (uint32_t)(older.v >> (8 * i)) & 0xFFu;
+      if ((int)r.m < K && lutb_find(newer.v, (int)newer.m, b) == (int)newer.m) { r.v |= (uint64_t)b << (8 * r.m); r.m++; }
+    }
+  }
+  return r;
+}
+// conversions (global-memory records use the generic layout)
+HSRLE_HD void lut_from(LutB &d, const Lut &s) { d.v = 0; HSRLE_UNROLL for (int i = 0; i < 7; i++) d.v |= (s.s[i] & 0xFFull) << (8 * i); }
+HSRLE_HD void lut_from(Lut &d, const Lut &s) { d = s; }
+HSRLE_HD void lut_to(Lut &d, const LutB &s) { HSRLE_UNROLL for (int i = 0; i < 7; i++) d.s[i] = (s.v >> (8 * i)) & 0xFFull; }
+HSRLE_HD void lut_to(Lut &d, const Lut &s) { d = s; }
+HSRLE_HD void lutagg_from(LutAggB &d, const LutAgg &s) { d.m = s.m; d.pad = 0; d.v = 0; HSRLE_UNROLL for (int i = 0; i < 7; i++) d.v |= (s.s[i] & 0xFFull) << (8 * i); }
+HSRLE_HD void lutagg_from(LutAgg &d, const LutAgg &s) { d = s; }
+HSRLE_HD void lutagg_to(LutAgg &d, const LutAggB &s) { d.m = s.m; HSRLE_UNROLL for (int i = 0; i < 7; i++) d.s[i] = (s.v >> (8 * i)) & 0xFFull; }
+HSRLE_HD void lutagg_to(LutAgg &d, const LutAgg &s) { d = s; }
+HSRLE_HD uint64_t lut_entry(const LutB &l, int i) { return (l.v >> (8 * i)) & 0xFFull; }
+HSRLE_HD uint64_t lut_entry(const Lut &l, int i)
+{
+  uint64_t v = l.s[0];
+  HSRLE_UNROLL
+  for (int k = 1; k < 7; k++) if (k == i) v = l.s[k];
+  return v;
+}
+HSRLE_HD uint64_t lutagg_entry(const LutAggB &a, int i) { return (a.v >> (8 * i)) & 0xFFull; }
+HSRLE_HD uint64_t lutagg_entry(const LutAgg &a, int i)
+{
+  uint64_t v = a.s[0];
+  HSRLE_UNROLL
+  for (int k = 1; k < 7; k++) if (k == i) v = a.s[k];
+  return v;
+}
+template <int W> struct LutRep { using L = Lut; using A = LutAgg; };
+template <> struct LutRep<1> { using L = LutB; using A = LutAggB; };
+
+// ------------------------------------------------------------------------------------------------
 // Encoder: evaluate one match-mask run [a,b) (M[p]==1 for a<=p<b, maximal, b-a >= sp.minM).
 // Returns EV_* flags.  With EV_EMIT, [s,e) is the run, `h` its header bytes (everything before the
 // literal), and the literal is in[lastBefore, s).  State is advanced either way.
@@ -262,9 +361,9 @@ enum : uint32_t { EV_VALID = 1, EV_EMIT = 2, EV_SYMSET = 4, EV_STATE_MASK = 7,
                   EV_MARG = 8,           // LUT codecs: the decision would flip between "symbol in the table" and "not in the table"
                   EV_IDX_SHIFT = 8 };    // LUT codecs: table index of the symbol (K = absent) in bits 8..10
 // `sym0` = the W input bytes in[a-W, a) (the first period of the run the mask run [a,b) belongs to).
-template <class Sink>
-HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a, uint32_t b, AutoState &st, Lut &lut, LutAgg *agg,
-                       uint32_t &s, uint32_t &e, Sink &h)
+template <class Sink, class LutT, class AggT>
+HSRLE_HD uint32_t enc_eval_t(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a, uint32_t b, AutoState &st, LutT &lut, AggT *agg,
+                         uint32_t &s, uint32_t &e, Sink &h)
 {
   const int W = sp.W;
   if (W == 1) { s = a - 1; e = b; }
@@ -346,6 +445,12 @@ HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a
   else { if (rng <= 255) h.put8(rng); else { h.put8(0); h.put32(rng); } }
   st.last = e;
   return EV_VALID | EV_EMIT | (symSet ? EV_SYMSET : 0u);
+}
+template <class Sink>
+HSRLE_HD uint32_t enc_eval(const Spec &sp, uint64_t sym0, uint32_t n, uint32_t a, uint32_t b, AutoState &st, Lut &lut, LutAgg *agg,
+                       uint32_t &s, uint32_t &e, Sink &h)
+{
+  return enc_eval_t<Sink, Lut, LutAgg>(sp, sym0, n, a, b, st, lut, agg, s, e, h);
 }
 
 // Terminator written after the last token; L = trailing literal length (n - last).

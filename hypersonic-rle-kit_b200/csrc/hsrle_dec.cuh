@@ -1,78 +1,82 @@
-// hsrle_dec.cuh -- decoder pipeline of the B200 extreme-RLE codec.
+// hsrle_dec.cuh -- decoder pipeline of the B200 extreme-RLE codec (two launches).
 //
-// The stream has no sync markers: token k starts where token k-1 ends.  The decoder finds
-// the token chain speculatively per super-chunk (SC, 16 KiB of stream) and resolves it with a merge:
+// The stream has no sync markers: token k starts where token k-1 ends.  The decoder finds the token chain
+// speculatively per chunk (16 KiB of stream) and resolves it with a merge of windowed exit maps:
 //
-//   D1  k_dec_map<codec>     per SC: parse a token at EVERY byte offset; a reverse sweep per 128-byte
-//                            mini-block gives "where does a chain that starts here leave the mini-block"
-//                            (exTab, kept for D3); a two-level in-place finalisation (warp-blocks, then the
-//                            SC) turns that into "where does it leave the SC" for every offset (finTab,
-//                            absolute positions).  The first DEC_WIN entries of an SC's finTab row are its
-//                            windowed exit map: token chains re-enter the next SC within a few hundred
-//                            bytes of its start unless a long literal spans the boundary.
-//   D2a k_dec_compose        per segment of DEC_SEG SCs, in reverse SC order: sufExit[c][w] = where the chain
-//                            that enters SC c at window offset w leaves the SEGMENT.  Chains that enter an SC
-//                            beyond its window (after a long literal) take one finTab look-up instead.
-//   D2b k_dec_resolve        one CTA: thread 0 chains the segments from the stream start (one look-up per
-//                            segment, one more per long-literal entry), then one thread per segment walks
-//                            its SCs forward through finTab and records every SC's true entry.
-//   D3a k_dec_walk<codec>    per SC: mark the true chain (entry into every mini-block, hopping through D1's
-//                            exit table), walk the tokens of every mini-block in parallel: output bytes, token
-//                            count, symbol / LUT state transform of the SC.
-//   D3s k_dec_scan           one CTA: exclusive scan of the SC aggregates (output offset, incoming symbol
-//                            state); final validation (terminator seen, total == uncompressedLength).
-//   D3b k_dec_expand<codec>  per SC: token records (output offset, literal source, run symbol), then one
-//                            16-byte aligned output vector per thread and step (literal gather / period-W
-//                            run fill).
+//   K1  k_dec_map<codec>   one CTA per chunk.  The chunk image arrives in shared memory by a 1-D bulk copy (TMA); a token is
+//                          parsed at EVERY byte offset; a blocked reverse sweep turns "where does the token at p end" into
+//                          "where does the chain that starts at p leave its 64 / 128 / 256 / 512-byte block", then -- only for
+//                          the first DEC_WIN offsets of every 1-KiB sub-chunk, the only places a chain can enter it unless a
+//                          long literal spans the boundary -- "... its sub-chunk" and "... the chunk".  Nothing per-position
+//                          leaves the SM: the chunk publishes its 16 windowed sub-chunk exit rows (subMap, u16 codes) and one
+//                          windowed chunk exit row (chunkMap, absolute positions).
+//                          The last CTA of every 32-chunk segment composes the segment's rows in reverse (sufMap: where does the
+//                          chain entering chunk c at window offset w leave the SEGMENT, or land outside a window), and the last
+//                          CTA of all follows the true chain from the stream start through those rows -- one look-up per
+//                          segment, rows staged in shared memory; out-of-window landings (after a long literal) continue by
+//                          parsing -- and leaves an ANCHOR (the exact position of a true token start) in every chunk it visits.
+//   K2  k_dec_emit<codec>  persistent CTAs take chunks in order.  The chunk's first true token start follows from the nearest
+//                          anchor (a few window-row hops); 16 lanes walk the chunk's 16 sub-chunks from their entries (sub-chunk
+//                          rows), giving per-token records, output bytes and symbol / LUT state of the chunk; a decoupled
+//                          look-back over the chunks yields the output offset and incoming symbol state; the tokens are
+//                          expanded into a 16-KiB shared-memory image of the output (byte-exact, any alignment) that is flushed
+//                          with aligned 16-byte stores.  Token parts that span whole output tiles of 256 KiB and more become
+//                          grid-wide operations every idle CTA helps with (literal source staged by bulk copies).
 //
-// Reference behaviour restated (never copied): token parse src/rleX_extreme_cpu_decode.h:43-163,
-// src/rleX_Xsl.h:580-784, src/rle8_extreme_cpu.h:1558-1632,2020-2087; header checks
-// src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91.
+// Reference behaviour restated (never copied): token parse src/rleX_extreme_cpu_decode.h:43-163, src/rleX_Xsl.h:580-784,
+// src/rle8_extreme_cpu.h:1558-1632,2020-2087; header checks src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91; the
+// copy / fill kit src/rleX_extreme_common.h:32-312 is replaced by the shared-memory image and wide stores.
 #pragma once
 #include "hsrle_core.cuh"
 #include "hsrle_enc.cuh"   // ST_* status codes
 
 namespace hsrle {
 
-constexpr uint32_t DEC_SCB = 16384;       // stream bytes per super-chunk
-constexpr uint32_t DEC_MB = 128;          // mini-block bytes (one thread sweeps one mini-block)
-constexpr int DEC_T = DEC_SCB / DEC_MB;   // 128 threads per SC
-constexpr uint32_t DEC_PAD = 32;          // readable bytes after the SC in shared memory (longest token header)
-constexpr uint32_t DEC_WIN = 512;         // entry window of an SC
-constexpr uint32_t DEC_SEG = 32;          // SCs per segment
-constexpr int DEC_GROUP = DEC_T;          // look-back group (thread 0: inclusive prefix, threads 1..: aggregates)
-constexpr uint32_t DEC_TOKCAP = 1024;     // token records kept in shared memory per expansion pass
+constexpr uint32_t DEC_CB = 16384;        // chunk: stream bytes per CTA step
+constexpr uint32_t DEC_SB = 1024;         // sub-chunk: the unit one lane walks in K2
+constexpr int DEC_NSUB = (int)(DEC_CB / DEC_SB);
+constexpr uint32_t DEC_WIN = 288;         // entry window: a token with a 1-byte range field ends < 8 + 11 + 254 bytes after its start
+constexpr uint32_t DEC_SEG = 32;          // chunks per segment
+constexpr uint32_t DEC_IMG_PAD = 512;     // stream bytes loaded after the chunk (token heads and short literals that straddle its end)
+constexpr uint32_t DEC_TILE = 16384;      // output image bytes per expansion step
+constexpr uint32_t DEC_NSLOT = 1024;      // token records per expansion pass
+constexpr uint32_t DEC_HUGE_TILES = 16;   // a token part covering at least this many whole tiles is a grid-wide operation
+constexpr uint32_t DEC_BIG_PIECE = 65536; // bytes of a grid-wide operation one CTA takes at a time
 
 constexpr uint32_t POS_END = 0xFFFFFFFFu; // chain reached the terminator
 constexpr uint32_t POS_BAD = 0xFFFFFFFEu; // chain ran into an unparsable position
-constexpr uint32_t POS_MISS = 0xFFFFFFFDu; // chain entered an SC outside its window (resolved by the slow path)
-constexpr uint32_t POS_NONE = 0xFFFFFFFCu; // no token starts in this SC / segment
+constexpr uint32_t POS_NONE = 0xFFFFFFFCu; // no token starts here
 constexpr uint32_t POS_SPECIAL = 0xFFFFFFF0u;
 
-// exit codes of the per-position table (u16, relative to the SC start)
+// exit codes of the per-position tables (u16, relative to the chunk start)
 constexpr uint32_t EX_FAR = 0x8000u;      // first code that is not a position inside [c0, c0 + 0x8000)
 constexpr uint32_t EX_END = 0x8000u, EX_BAD = 0x8001u;
-constexpr uint32_t EX_FARP = 0xC000u;     // | offset of the far-jumping token (its absolute exit: farTab)
+constexpr uint32_t EX_FARP = 0xC000u;     // | offset of the token that jumps beyond c0 + 0x7FFF (its exit: parse it again)
 
-struct DecScalars
+struct DecScalars                         // written once per call by CTA 0 of K1 (header check)
 {
   uint32_t n, clen, first, single, status;
   uint32_t singleSym;
-  uint32_t endSeen;
+};
+struct DecCounters                        // zeroed per call
+{
+  uint32_t segsDone;                      // K1: segments composed
+  uint32_t chainBad;                      // K1 resolver: the true chain does not reach the terminator
+  uint32_t ticket, chunksDone;            // K2: dynamic chunk ids, chunks finished
+  uint32_t emitBad, endSeen;              // K2: unparsable token on the true chain / terminator seen
+  uint32_t nBig;                          // grid-wide operations registered
   uint32_t nTok;
-  uint32_t segTicket;                     // k_dec_chain: dynamic segment ids
-  uint32_t ticket, done;                  // k_dec_emit: dynamic SC ids, CTAs finished
-  uint32_t emitBad;                       // k_dec_emit met an unparsable token on the true chain
-  uint32_t nHuge, nMed;                   // long operations handed to k_dec_big
   unsigned long long outTotal;            // output bytes of all tokens
 };
 
-// a long literal copy (kind 0: src = stream position of the first byte) or run fill (kind 1: src = output position
-// where the run starts, sym = its first period) of nv whole 16-byte output vectors starting at vector v0
+// a grid-wide literal copy (kind 0: src = stream position of the byte that lands at output byte dst) or run fill (kind 1:
+// src = output position where the run starts, sym = its first period) of `len` output bytes starting at the 16-byte aligned dst
 struct DecBigOp
 {
-  uint32_t v0, nv, src, kind;
   uint64_t sym;
+  uint32_t dst, len, src, kind;
+  uint32_t next;                          // pieces handed out
+  uint32_t ready;                         // published
 };
 
 // net effect of a token sequence on the K-entry LUT (decoder side): entry i of the table afterwards is either the
@@ -153,18 +157,17 @@ HSRLE_HD void lutxf_apply(const LutXf &x, int K, int W, const uint8_t *stream, c
   }
 }
 
-// what a token sequence contributes to the decoder state: output bytes, token count, symbol register
+// what a token sequence contributes to the decoder state: output bytes, token count, symbol register / table
 template <int K> struct DecAgg
 {
   uint64_t out;
   uint32_t ntok;
-  uint32_t has;         // K == 0: the sequence set the symbol register
-  uint64_t sym;
+  uint32_t symPos;      // K == 0: stream position of the last explicit symbol of the sequence (0: none)
   LutXf xf;             // K > 0
 };
 template <int K> HSRLE_HD DecAgg<K> decagg_identity()
 {
-  DecAgg<K> a; a.out = 0; a.ntok = 0; a.has = 0; a.sym = 0;
+  DecAgg<K> a; a.out = 0; a.ntok = 0; a.symPos = 0;
   if (K) lutxf_identity(a.xf);
   return a;
 }
@@ -172,7 +175,7 @@ template <int K> HSRLE_HD DecAgg<K> decagg_combine(const DecAgg<K> &older, const
 {
   DecAgg<K> r;
   r.out = older.out + newer.out; r.ntok = older.ntok + newer.ntok;
-  if (newer.has) { r.has = 1; r.sym = newer.sym; } else { r.has = older.has; r.sym = older.sym; }
+  r.symPos = newer.symPos ? newer.symPos : older.symPos;
   if (K) r.xf = lutxf_compose(older.xf, newer.xf, K);
   return r;
 }
@@ -181,28 +184,26 @@ struct DecBufs
 {
   const uint8_t *in; uint32_t inSize;
   uint8_t *out; uint32_t outSize;
-  uint32_t nSC, nSeg;
-  uint16_t *exTab;          // [nSC][DEC_SCB]   per-position mini-block exit tables (D1 -> D3)
-  uint16_t *scTab;          // [nSC][DEC_SCB]   per-position SC exit codes (D1 -> D2)
-  uint32_t *farTab;         // [nSC][DEC_SCB]   absolute exit of the far-jumping token at that position (sparse)
-  uint32_t *winTab;         // [nSC][DEC_WIN]   absolute SC exits of the window positions
-  uint32_t *scSkip;         // [nSC]  1: D1's scout found the SC jumped over by a true token (constant tables); cleared per call
-  uint32_t *sufExit;        // [nSC][DEC_WIN]   exit of the segment when SC c is entered at window offset w
-  uint32_t *flagSeg, *chainFlag;   // [nSeg] "rows published" / "chain position published" (zeroed per call)
-  uint32_t *chainPos;       // [nSeg] first position of the true chain at or after the start of the segment (or its end code)
-  uint32_t *scEntry;        // [nSC]  true entry (absolute stream position) or POS_NONE
-  void *aggBuf, *incBuf;    // [nSC] DecAgg<K>: per-SC totals; inclusive prefixes (last SC of every look-back group)
-  uint32_t *flagAgg, *flagInc;   // [nSC] "published" flags of the two (zeroed per call)
-  DecBigOp *medList, *hugeList;  // long operations for k_dec_big
+  uint32_t nChunks, nSeg;   // capacities from inSize (the header's compressedLength may be smaller)
+  uint32_t emitGrid;        // CTAs of K2
   DecScalars *sc;
+  DecCounters *cnt;         // --- zeroed per call from here ...
+  uint32_t *segCount;       // [nSeg]    chunks of the segment that published their rows
+  uint32_t *anchorAt;       // [nChunks] position of the first true token start the resolver saw in the chunk (0: none)
+  uint32_t *flagAgg;        // [nChunks] look-back: 1 = aggregate published, 2 = inclusive prefix published   ... to here
+  uint32_t *chunkMap;       // [nChunks][DEC_WIN] absolute exit of the chunk when entered at window offset w
+  uint32_t *sufMap;         // [nChunks][DEC_WIN] ... of the SEGMENT (or the first out-of-window landing inside it)
+  uint16_t *subMap;         // [nChunks][DEC_NSUB][DEC_WIN] exit codes of the sub-chunks
+  void *aggBuf, *incBuf;    // [nChunks] DecAgg<K>: per-chunk totals / inclusive prefixes
+  DecBigOp *bigList;
+  uint32_t bigCap;
   uint32_t *dResult;
 };
 
 // header check -- src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91 (every CTA evaluates it itself)
 HSRLE_HD void dec_header(const Spec &sp, const uint8_t *in, uint32_t inSize, uint32_t outSize, DecScalars &sc)
 {
-  sc.status = ST_OK; sc.single = 0; sc.singleSym = 0; sc.endSeen = 0; sc.nTok = 0; sc.n = 0; sc.clen = 0; sc.first = sp.hdr;
-  sc.segTicket = 0; sc.ticket = 0; sc.done = 0; sc.emitBad = 0; sc.nHuge = 0; sc.nMed = 0; sc.outTotal = 0;
+  sc.status = ST_OK; sc.single = 0; sc.singleSym = 0; sc.n = 0; sc.clen = 0; sc.first = sp.hdr;
   if (inSize < (uint32_t)sp.hdr) { sc.status = ST_BADARG; return; }
   sc.n = load32(in); sc.clen = load32(in + 4);
   if (sc.n > outSize || sc.clen > inSize || sc.clen < (uint32_t)sp.hdr || sc.clen >= POS_SPECIAL) { sc.status = ST_BADARG; return; }

@@ -10,9 +10,10 @@ namespace hsrle {
 struct EncKernels
 {
   void (*scan)(const EncBufs);
-  void (*autom)(const EncBufs, int);
+  void (*autom)(const EncBufs);
+  void (*fix)(const EncBufs, int, int);
   void (*emit)(const EncBufs);
-  size_t autoSmem, emitSmem;
+  size_t autoSmem, fixSmem, emitSmem;
   int symBytes;           // 4 or 8: element size of EncBufs::runSym
   int minM;
 };

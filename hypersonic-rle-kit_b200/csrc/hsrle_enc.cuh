@@ -38,14 +38,16 @@ constexpr int E2_SCR = E2_T * E2_CH;      // records per super-chunk
 constexpr int E2L_CH = 16;                // LUT codecs: records per lane -- one warp owns a whole super-chunk
 static_assert(E2L_CH * 32 == E2_SCR && E2L_CH % E2_CH == 0, "a warp covers one super-chunk");
 constexpr uint32_t SCF_SENS = 1;          // scFlags: a decision of the super-chunk depended on the incoming LUT
+constexpr int FIX_T = 512;                // threads of the single-CTA verify / repair kernel (k_enc_fix)
+constexpr int FIX_W = FIX_T / 32;
+constexpr int FIX_LIST = 2048;            // dirty super-chunks listed per round (more: the warps scan the dirty flags)
 constexpr int E2_MAXIT = 16;              // in-CTA fixed-point rounds before the in-CTA sequential pass
-constexpr int E2_ROUNDS = 6;              // grid-level rounds (the last one ends with the sequential repair); rounds without dirt
-                                          // return at once.  3 rounds left 14-21 dirty super-chunks on short-run streams read with
-                                          // a wider symbol (rle24_byte_packed, rle32_sym: few tokens, the state passes through many
-                                          // super-chunks), and the sequential repair then re-ran 770-1,170 of them one by one (3-4 ms)
-constexpr int E2L1_ROUNDS = 24;           // ... for the 8-bit LUT codecs, whose table has long-range memory:
-                                          // a changed table travels one super-chunk per round; rounds without dirt return at once
-constexpr int E2_MAXROUNDS = 24;
+constexpr int E2_ROUNDS = 64;             // verify / repair rounds inside k_enc_fix before the exact sequential repair takes over.  A
+                                          // wrong state guess travels one super-chunk per round: short-run streams read with a wider
+                                          // symbol (rle24_byte_packed, rle32_sym: few tokens, the state passes through many super-chunks)
+                                          // need a dozen rounds ...
+constexpr int E2L1_ROUNDS = 512;          // ... and the 8-bit LUT codecs, whose table has long-range memory, 40-90
+constexpr int E2_MAXROUNDS = 24;          // (size of the diagnostic arrays in EncScalars)
 HSRLE_HDC int enc_rounds(int W, int K) { return (K != 0 && W == 1) ? E2L1_ROUNDS : E2_ROUNDS; }
 constexpr int E2_NQ = 6;                  // LUT codecs: recorded table queries per super-chunk (more: always re-run)
 constexpr uint32_t MED_COPY = 256;        // literals at least this long go to the grid-wide copy kernel (one warp each)
@@ -66,6 +68,7 @@ struct EncScalars
   uint32_t serialSC;                      // super-chunks repaired sequentially (diagnostics)
   uint32_t innerSerial;                   // super-chunks that needed the in-CTA sequential pass (diagnostics)
   uint64_t tokBytes;                      // sum over tokens of header + literal bytes
+  uint32_t fixCmd, fixRound, fixTicket, fixDone;   // k_enc_fix: helpers leave / grid round number / ticket counter / tickets completed
   uint32_t endShift;                      // slices: start record i pairs with end record i + endShift (hsrle_slice.cuh)
   uint32_t nStarts, nEnds;                // slices: records found by the scan
 };
@@ -108,10 +111,10 @@ HSRLE_HD ChunkSum chunksum_combine(const ChunkSum &older, const ChunkSum &newer)
 HSRLE_HD AutoState enc_initial_state() { AutoState s; s.cursor = 0; s.last = 0; s.lastSym = 0; return s; }
 
 // scan element: what a segment of records does to the automaton state, plus its token totals
-template <int K> struct SegSum
+template <int K, class AggT = LutAgg> struct SegSum
 {
   ChunkSum cs;
-  LutAgg agg;           // only meaningful for K > 0
+  AggT agg;             // only meaningful for K > 0 (LutAgg, or the packed LutAggB for 8-bit symbols)
   uint64_t bytes;
   uint32_t ntok;
 };
@@ -204,20 +207,22 @@ template <int MINM> HSRLE_HD void m16_boundaries(uint32_t A, uint32_t &starts, u
 }
 
 // ---------------------------------------------------------------- E2 helpers (host+device)
-template <int K> HSRLE_HD SegSum<K> segsum_identity()
+HSRLE_HD void lutagg_clear(LutAgg &a) { a.m = 0; }
+HSRLE_HD void lutagg_clear(LutAggB &a) { a.m = 0; a.pad = 0; a.v = 0; }
+template <int K, class AggT = LutAgg> HSRLE_HD SegSum<K, AggT> segsum_identity()
 {
-  SegSum<K> s; s.cs = chunksum_identity(); s.agg.m = 0; s.bytes = 0; s.ntok = 0;
+  SegSum<K, AggT> s; s.cs = chunksum_identity(); lutagg_clear(s.agg); s.bytes = 0; s.ntok = 0;
   return s;
 }
-template <int K> HSRLE_HD SegSum<K> segsum_combine(const SegSum<K> &older, const SegSum<K> &newer)
+template <int K, class AggT> HSRLE_HD SegSum<K, AggT> segsum_combine(const SegSum<K, AggT> &older, const SegSum<K, AggT> &newer)
 {
-  SegSum<K> r;
+  SegSum<K, AggT> r;
   r.cs = chunksum_combine(older.cs, newer.cs);
-  if (K) r.agg = lutagg_combine(older.agg, newer.agg, K); else r.agg.m = 0;
+  if (K) r.agg = lutagg_combine(older.agg, newer.agg, K); else lutagg_clear(r.agg);
   r.bytes = older.bytes + newer.bytes; r.ntok = older.ntok + newer.ntok;
   return r;
 }
-template <int K> HSRLE_HD void segsum_apply(AutoState &st, Lut &lut, const SegSum<K> &s)
+template <int K, class AggT, class LutT> HSRLE_HD void segsum_apply(AutoState &st, LutT &lut, const SegSum<K, AggT> &s)
 {
   chunksum_apply(st, s.cs);
   if (K) lut_apply(lut, K, s.agg);
@@ -229,27 +234,28 @@ template <int K> HSRLE_HD void segsum_apply(AutoState &st, Lut &lut, const SegSu
 // decisions was marginal (EV_MARG) for a symbol outside the known front part: only such "sensitive" super-chunks
 // have to be re-run when the guess turns out wrong.  What does change with the incoming table is whether the first
 // emission of each of the <= K symbols of scFo found its symbol in the table (no symbol bytes) or not (W bytes).
-HSRLE_HD uint32_t enc_fo_misses(const Lut &fo, uint32_t m, int K, const Lut &incoming)
+template <class LutT> HSRLE_HD uint32_t enc_fo_misses(const LutT &fo, uint32_t m, int K, const LutT &incoming)
 {
-  Lut l = incoming;
+  LutT l = incoming;
   uint32_t misses = 0;
   HSRLE_UNROLL
   for (int i = 0; i < 7; i++)
   {
     if (i < K && i < (int)m)
     {
-      const int idx = lut_find(l, K, fo.s[i]);
+      const uint64_t f = lut_entry(fo, i);
+      const int idx = lut_find(l, K, f);
       if (idx == K) misses++;
-      lut_touch(l, K, idx, fo.s[i]);
+      lut_touch(l, K, idx, f);
     }
   }
   return misses;
 }
 // would any recorded query of a super-chunk get another answer if its incoming table were `incoming`?
-HSRLE_HD bool enc_queries_differ(const ScQueries &q, const Lut &fo, uint32_t m, int K, const Lut &incoming)
+template <class LutT> HSRLE_HD bool enc_queries_differ(const ScQueries &q, const LutT &fo, uint32_t m, int K, const LutT &incoming)
 {
   if (q.n > (uint32_t)E2_NQ) return true;
-  Lut l = incoming;
+  LutT l = incoming;
   bool diff = false;
   HSRLE_UNROLL
   for (int k = 0; k < 7; k++)
@@ -259,7 +265,7 @@ HSRLE_HD bool enc_queries_differ(const ScQueries &q, const Lut &fo, uint32_t m, 
       HSRLE_UNROLL
       for (int i = 0; i < E2_NQ; i++)
         if ((uint32_t)i < q.n && q.known[i] == (uint8_t)k) diff = diff || ((lut_find(l, K, q.sym[i]) != K) != (q.hit[i] != 0));
-      if (k < (int)m) { const int idx = lut_find(l, K, fo.s[k]); lut_touch(l, K, idx, fo.s[k]); }
+      if (k < (int)m) { const uint64_t f = lut_entry(fo, k); const int idx = lut_find(l, K, f); lut_touch(l, K, idx, f); }
     }
   }
   return diff;
@@ -278,7 +284,7 @@ HSRLE_HD void enc_chunk_lut(Lut &chunkLut, uint32_t known, int K, const Lut &scI
 
 // state guess for a chunk whose predecessor records are unknown: "a run was just emitted right before
 // the first candidate", initial LUT
-HSRLE_HD void enc_neutral_state(const Spec &sp, uint32_t firstA, AutoState &st, Lut &lut)
+template <class LutT> HSRLE_HD void enc_neutral_state(const Spec &sp, uint32_t firstA, AutoState &st, LutT &lut)
 {
   st = enc_initial_state();
   st.last = firstA - sp.W;

@@ -38,6 +38,16 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_volatile_u32g(const uint32_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u32g(uint32_t *p, uint32_t v)
+{
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ================================================================================================
 // E1: candidate scan, single pass.
@@ -233,16 +243,18 @@ __device__ __forceinline__ void enc_push_copy(const EncBufs &B, uint32_t dst, ui
 __device__ __forceinline__ int rec_slot(int j) { return j + j / E2_CH; }
 
 // state the automaton starts from: the stream's initial state, or the slice's incoming state (hsrle_slice.cuh)
-__device__ __forceinline__ void enc_stream_incoming(const EncBufs &B, int W, AutoState &st, Lut &lut)
+template <class LutT> __device__ __forceinline__ void enc_stream_incoming(const EncBufs &B, int W, AutoState &st, LutT &lut)
 {
-  if (B.sliceMode) { st = B.sliceIn->st; lut = B.sliceIn->lut; }
+  if (B.sliceMode) { st = B.sliceIn->st; lut_from(lut, B.sliceIn->lut); }
   else { st = enc_initial_state(); lut_init(lut, W); }
 }
 
 template <int W, int BA, int V, class SymT> struct EncCta
 {
   static constexpr int K = (V == V_LUT3) ? 3 : (V == V_LUT7 ? 7 : 0);
-  using Seg = SegSum<K>;
+  using LutR = typename LutRep<W>::L;     // register representation of the table: one packed word for 8-bit symbols
+  using AggR = typename LutRep<W>::A;
+  using Seg = SegSum<K, AggR>;
   static constexpr int NREC = E2_SCR + E2_WARM;               // with the warm-up halo
   static constexpr int NSLOT = NREC + NREC / E2_CH + 1;
   // one warp per super-chunk, E2L_CH records per lane: a 32-element warp scan per fixed-point step, no block barrier
@@ -255,20 +267,22 @@ template <int W, int BA, int V, class SymT> struct EncCta
   {
     uint32_t a[NSLOTL], b[NSLOTL];
     SymT sym[NSLOTL];
-    AutoState serSt[32]; Lut serLut[K ? 32 : 1];               // states produced by the sequential pass
+    AutoState serSt[32]; LutR serLut[K ? 32 : 1];              // states produced by the sequential pass
     AutoState snap[K ? 1 : 32][E2L_CH / E2_CH];                 // plain/packed: per lane, the state at every E3 chunk boundary
     uint64_t fo[8];
     uint32_t foMiss, sens;
     ScQueries q;
   };
-  struct Smem
+  struct Smem { WarpRecs r[NW]; };                            // round 0: one super-chunk per warp
+  struct FixSmem                                                // the single-CTA verify / repair kernel
   {
-    WarpRecs r[NW];
-    Seg warpTot[E2_T / 32];
+    WarpRecs r[FIX_W];
+    Seg warpTot[FIX_W];
     Seg bcTot;
-    AutoState bcSt; Lut bcLut;                                  // broadcast slots
-    uint64_t warpBytes[E2_T / 32];
-    uint32_t flag;
+    AutoState bcSt; LutR bcLut;                                 // broadcast slots
+    uint64_t warpBytes[FIX_W];
+    uint32_t nDirty, firstDirty, nList;
+    uint32_t list[FIX_LIST];                                    // dirty super-chunks of the round (when they fit)
   };
 
   // evaluate records [j0,j1) (local indices; record j lives in slot j + j / CHS) from (st,lut); returns the segment summary
@@ -276,10 +290,10 @@ template <int W, int BA, int V, class SymT> struct EncCta
   // only then can the range's decisions depend on the table it started from (hsrle_enc.cuh)
   template <int CHS>
   static __device__ __forceinline__ Seg eval_range(const uint32_t *ra, const uint32_t *rb, const SymT *rs, uint32_t n, uint32_t floor, int j0, int j1,
-                                                   AutoState &st, Lut &lut, uint32_t *sens0 = nullptr, AutoState *snap = nullptr)
+                                                   AutoState &st, LutR &lut, uint32_t *sens0 = nullptr, AutoState *snap = nullptr)
   {
     constexpr Spec sp = make_spec(W, BA, V);
-    Seg r = segsum_identity<K>();
+    Seg r = segsum_identity<K, AggR>();
     uint32_t fl = 0, known = 0, sens = 0;
     for (int j = j0; j < j1; j++)
     {
@@ -287,7 +301,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       const int q = j + j / CHS;
       uint32_t s, e; CountSink h;
       const uint32_t lastBefore = st.last;
-      const uint32_t ev = enc_eval(sp, (uint64_t)rs[q], n, ra[q], rb[q], st, lut, K ? &r.agg : nullptr, s, e, h);
+      const uint32_t ev = enc_eval_t<CountSink, LutR, AggR>(sp, (uint64_t)rs[q], n, ra[q], rb[q], st, lut, K ? &r.agg : (AggR *)nullptr, s, e, h);
       fl |= ev & EV_STATE_MASK;
       if (ev & EV_EMIT) { r.bytes += h.len + slice_lit_len(lastBefore, s, floor); r.ntok++; }
       if constexpr (K != 0)
@@ -302,7 +316,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
   }
 
   // exclusive scan of the per-thread segment summaries over the CTA; `total` = combination of all
-  static __device__ __forceinline__ Seg block_excl_scan(Smem &S, const Seg &mine, Seg &total)
+  static __device__ __forceinline__ Seg block_excl_scan(FixSmem &S, const Seg &mine, Seg &total)
   {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Seg inc = mine;
@@ -310,26 +324,26 @@ template <int W, int BA, int V, class SymT> struct EncCta
     for (int d = 1; d < 32; d <<= 1)
     {
       const Seg o = shfl_up_t(inc, d);
-      if (lane >= d) inc = segsum_combine<K>(o, inc);
+      if (lane >= d) inc = segsum_combine(o, inc);
     }
     if (lane == 31) S.warpTot[warp] = inc;
     Seg ex = shfl_up_t(inc, 1);
-    if (lane == 0) ex = segsum_identity<K>();
+    if (lane == 0) ex = segsum_identity<K, AggR>();
     __syncthreads();
-    Seg pre = segsum_identity<K>();
-    total = segsum_identity<K>();
-#pragma unroll
-    for (int w = 0; w < E2_T / 32; w++)
+    Seg pre = segsum_identity<K, AggR>();
+    total = segsum_identity<K, AggR>();
+#pragma unroll 1
+    for (int w = 0; w < FIX_W; w++)
     {
       const Seg t = S.warpTot[w];
-      if (w < warp) pre = segsum_combine<K>(pre, t);
-      total = segsum_combine<K>(total, t);
+      if (w < warp) pre = segsum_combine(pre, t);
+      total = segsum_combine(total, t);
     }
     __syncthreads();
-    return segsum_combine<K>(pre, ex);
+    return segsum_combine(pre, ex);
   }
 
-  static __device__ __forceinline__ bool state_differs(const AutoState &a, const Lut &la, const AutoState &b, const Lut &lb)
+  static __device__ __forceinline__ bool state_differs(const AutoState &a, const LutR &la, const AutoState &b, const LutR &lb)
   {
     bool d = (a != b);
     if (K) d = d || !lut_equal(la, lb, K);
@@ -349,18 +363,17 @@ template <int W, int BA, int V, class SymT> struct EncCta
     for (int d = 1; d < 32; d <<= 1)
     {
       const Seg o = shfl_up_t(inc, d);
-      if (lane >= d) inc = segsum_combine<K>(o, inc);
+      if (lane >= d) inc = segsum_combine(o, inc);
     }
     pre = shfl_up_t(inc, 1);
-    if (lane == 0) pre = segsum_identity<K>();
+    if (lane == 0) pre = segsum_identity<K, AggR>();
     total = shfl_idx_t(inc, 31);
   }
 
-  static __device__ void process(const EncBufs &B, Smem &S, uint32_t s, bool given, const AutoState &gSt, const Lut &gLut, Seg &totalOut)
+  static __device__ void process(const EncBufs &B, WarpRecs &R, uint32_t s, bool given, const AutoState &gSt, const LutR &gLut, Seg &totalOut)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     const int lane = threadIdx.x & 31;
-    WarpRecs &R = S.r[threadIdx.x >> 5];
     const uint32_t nRuns = B.sc->nRuns, n = B.n, floor = B.sliceLo, endShift = B.sc->endShift;
     const uint32_t lo = s * E2_SCR;
     const uint32_t cnt = min((uint32_t)E2_SCR, nRuns - lo);
@@ -379,21 +392,21 @@ template <int W, int BA, int V, class SymT> struct EncCta
     const int j1 = min(j0 + E2L_CH, E2_WARM + (int)cnt);
     const bool active = j0 < j1;
 
-    AutoState stIn; Lut lutIn;
+    AutoState stIn; LutR lutIn;
     if (lane == 0 && given) { stIn = gSt; lutIn = gLut; }
     else if (lane == 0 && s == 0) enc_stream_incoming(B, W, stIn, lutIn);
     else
     { // warm up over the preceding E2_WARM records from the neutral guess
       const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
       enc_neutral_state(sp, (active && w0 < j0) ? R.a[w0 + w0 / E2L_CH] : 0u, stIn, lutIn);
-      if (active && w0 < j0) { AutoState ws = stIn; Lut wl = lutIn; (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+      if (active && w0 < j0) { AutoState ws = stIn; LutR wl = lutIn; (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
     }
-    Seg mine = segsum_identity<K>();
+    Seg mine = segsum_identity<K, AggR>();
     uint32_t sens0 = 0;
     AutoState *const snapP = K ? nullptr : R.snap[K ? 0 : lane];   // plain/packed: the chunk states E3 needs fall out of the last evaluation
-    if (active) { AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP); }
+    if (active) { AutoState st = stIn; LutR lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP); }
     const AutoState st0 = shfl_idx_t(stIn, 0);
-    Lut lut0;
+    LutR lut0;
     if constexpr (K != 0) lut0 = shfl_idx_t(lutIn, 0); else lut_init(lut0, W);
 
     // fixed point of (scan -> compare -> re-run).  A lane whose decisions cannot depend on the table it started from
@@ -403,8 +416,8 @@ template <int W, int BA, int V, class SymT> struct EncCta
     for (int it = 0; it < E2_MAXIT; it++)
     {
       warp_scan(mine, pre, total);
-      AutoState want = st0; Lut wantLut = lut0;
-      segsum_apply<K>(want, wantLut, pre);
+      AutoState want = st0; LutR wantLut = lut0;
+      segsum_apply(want, wantLut, pre);
       int changed = 0;
       if (active && lane > 0)
       {
@@ -412,7 +425,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         if (want != stIn || (lutDiff && sens0))
         {
           stIn = want; lutIn = wantLut; changed = 1;
-          AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP);
+          AutoState st = stIn; LutR lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, &sens0, snapP);
         }
         else if (lutDiff) lutIn = wantLut;
       }
@@ -422,7 +435,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     { // exact sequential pass: lane 0 threads the state through every lane's records
       if (lane == 0)
       {
-        AutoState st = st0; Lut lut = lut0;
+        AutoState st = st0; LutR lut = lut0;
         for (int c = 0; c * E2L_CH < (int)cnt; c++)
         {
           R.serSt[c] = st; if (K) R.serLut[K ? c : 0] = lut;
@@ -435,7 +448,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       if (active)
       {
         stIn = R.serSt[lane]; if (K) lutIn = R.serLut[K ? lane : 0];
-        AutoState st = stIn; Lut lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, nullptr, snapP);
+        AutoState st = stIn; LutR lut = lutIn; mine = eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, j0, j1, st, lut, nullptr, snapP);
       }
       warp_scan(mine, pre, total);
     }
@@ -451,7 +464,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
     }
     else if (active)
     {
-      AutoState st = stIn; Lut lut = lutIn;
+      AutoState st = stIn; LutR lut = lutIn;
       uint32_t known = pre.agg.m, sensL = 0;
       uint64_t bytesL = 0;
       for (int j = j0; j < j1; j++)
@@ -460,12 +473,12 @@ template <int W, int BA, int V, class SymT> struct EncCta
         {
           const uint32_t chunk = s * E2_T + (uint32_t)(j - E2_WARM) / E2_CH;
           B.cIn[chunk] = st;
-          if (K) { B.cLut[chunk] = lut; B.cKnown[chunk] = (uint8_t)known; }
+          if (K) { lut_to(B.cLut[chunk], lut); B.cKnown[chunk] = (uint8_t)known; }
         }
         const int q = j + j / E2L_CH;
         uint32_t rs, re; CountSink h;
         const uint32_t lastBefore = st.last;
-        const uint32_t ev = enc_eval(sp, (uint64_t)R.sym[q], n, R.a[q], R.b[q], st, lut, nullptr, rs, re, h);
+        const uint32_t ev = enc_eval_t<CountSink, LutR, AggR>(sp, (uint64_t)R.sym[q], n, R.a[q], R.b[q], st, lut, (AggR *)nullptr, rs, re, h);
         if (ev & EV_EMIT) bytesL += h.len + slice_lit_len(lastBefore, rs, floor);
         if constexpr (K != 0)
         {
@@ -478,11 +491,11 @@ template <int W, int BA, int V, class SymT> struct EncCta
               const uint32_t slot = atomicAdd(&R.q.n, 1u);
               if (slot < (uint32_t)E2_NQ)
               {
-                R.q.sym[slot] = (ev & EV_EMIT) ? lut.s[0] : sym_rot((uint64_t)R.sym[q], W, rs - (R.a[q] - W));
+                R.q.sym[slot] = (ev & EV_EMIT) ? lut_front(lut) : sym_rot((uint64_t)R.sym[q], W, rs - (R.a[q] - W));
                 R.q.known[slot] = (uint8_t)known; R.q.hit[slot] = idx < (uint32_t)K ? 1 : 0;
               }
             }
-            if (ev & EV_EMIT) { R.fo[known] = lut.s[0]; if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
+            if (ev & EV_EMIT) { R.fo[known] = lut_front(lut); if (idx == (uint32_t)K) atomicAdd(&R.foMiss, 1u); known++; }
           }
         }
       }
@@ -504,21 +517,21 @@ template <int W, int BA, int V, class SymT> struct EncCta
       B.scBytes[s] = total.bytes - (uint64_t)W * R.foMiss; B.scTok[s] = total.ntok;
       if constexpr (K != 0)
       {
-        B.scAgg[s] = total.agg;
+        lutagg_to(B.scAgg[s], total.agg);
         Lut fo;
 #pragma unroll
         for (int i = 0; i < 7; i++) fo.s[i] = (i < K && i < (int)total.agg.m) ? R.fo[i] : 0ull;
         B.scFo[s] = fo; B.scFlags[s] = R.sens ? (uint8_t)SCF_SENS : (uint8_t)0;
         B.scQ[s] = R.q;
       }
-      if (!given) { B.scIn[s] = st0; if (K) B.scLut[s] = lut0; }
+      if (!given) { B.scIn[s] = st0; if (K) lut_to(B.scLut[s], lut0); }
       __threadfence();                                            // read by the round's last CTA
     }
     totalOut = total;
   }
 
   // ---- run by the last CTA of a round: scan of the super-chunk summaries, verification, finishing
-  static __device__ void finish(const EncBufs &B, const AutoState &fin, const Lut &finLut, uint64_t tokBytes, uint32_t nTok)
+  static __device__ void finish(const EncBufs &B, const AutoState &fin, const LutR &finLut, uint64_t tokBytes, uint32_t nTok)
   { // all threads call; thread 0 writes header/terminator, everybody copies a short trailing literal
     constexpr Spec sp = make_spec(W, BA, V);
     EncScalars &sc = *B.sc;
@@ -530,7 +543,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
         sc.tokBytes = tokBytes; sc.nTok = nTok;
         if (sc.status == ST_OK && (uint64_t)B.outBase + tokBytes + 64 > B.cap) sc.status = ST_OVERFLOW;
         SliceMsg &m = *B.msg;
-        m.out = fin; if (K) m.outLut = finLut; else lut_init(m.outLut, W);
+        m.out = fin; if (K) lut_to(m.outLut, finLut); else lut_init(m.outLut, W);
         m.tokBytes = tokBytes; m.status = sc.status;
         uint32_t *r = B.dResult;
         r[0] = 0; r[1] = sc.status; r[2] = sc.nRuns; r[3] = sc.nSC; r[4] = sc.serialSC; r[5] = sc.innerSerial; r[6] = 0; r[7] = sc.nDirty[0];
@@ -567,63 +580,86 @@ template <int W, int BA, int V, class SymT> struct EncCta
   }
 
   // would super-chunk s decide anything differently if its incoming table were `lut`?
-  static __device__ __forceinline__ bool lut_sensitive(const EncBufs &B, uint32_t s, const Lut &lut)
+  static __device__ __forceinline__ bool lut_sensitive(const EncBufs &B, uint32_t s, const LutR &lut)
   {
     if (!K || !(B.scFlags[s] & SCF_SENS)) return false;
-    return enc_queries_differ(B.scQ[s], B.scFo[s], B.scAgg[s].m, K, lut);
+    LutR fo; lut_from(fo, B.scFo[s]);
+    return enc_queries_differ(B.scQ[s], fo, B.scAgg[s].m, K, lut);
   }
 
   // exact token bytes of super-chunk s when its incoming table is `lut`
-  static __device__ __forceinline__ uint64_t sc_bytes(const EncBufs &B, uint32_t s, const Lut &lut)
+  static __device__ __forceinline__ uint64_t sc_bytes(const EncBufs &B, uint32_t s, const LutR &lut)
   {
     uint64_t b = B.scBytes[s];
-    if (K) { const uint32_t m = B.scAgg[s].m; if (m) b += (uint64_t)W * enc_fo_misses(B.scFo[s], m, K, lut); }
+    if (K) { const uint32_t m = B.scAgg[s].m; if (m) { LutR fo; lut_from(fo, B.scFo[s]); b += (uint64_t)W * enc_fo_misses(fo, m, K, lut); } }
     return b;
   }
-
-  static __device__ void scan_verify(const EncBufs &B, Smem &S, int round)
+  // a super-chunk's summary as a scan element
+  static __device__ __forceinline__ Seg load_seg(const EncBufs &B, uint32_t s, uint64_t bytes)
   {
-    EncScalars &sc = *B.sc;
-    const uint32_t nSC = sc.nSC;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    __shared__ uint32_t sDirty, sFirst;
-    if (t == 0) { sDirty = 0; sFirst = 0xFFFFFFFFu; }
-    const uint32_t per = (nSC + E2_T - 1) / E2_T;
+    Seg e; e.cs = B.scSum[s];
+    if (K) lutagg_from(e.agg, B.scAgg[s]); else lutagg_clear(e.agg);
+    e.bytes = bytes; e.ntok = B.scTok[s];
+    return e;
+  }
+
+  // ---- verification: scan of the super-chunk summaries, exact incoming state of every super-chunk, dirty marks.
+  //      Returns the number of dirty super-chunks (uniform); the indices of up to FIX_LIST of them are in S.list.
+  static __device__ uint32_t verify(const EncBufs &B, FixSmem &S, Seg &total)
+  {
+    const uint32_t nSC = B.sc->nSC;
+    const int t = threadIdx.x;
+    if (t == 0) { S.nDirty = 0; S.firstDirty = 0xFFFFFFFFu; S.nList = 0; }
+    const uint32_t per = (nSC + FIX_T - 1) / FIX_T;
     const uint32_t lo = min(nSC, (uint32_t)t * per), hi = min(nSC, lo + per);
-    // (1) states: scan of the summaries (token bytes follow in (3): for LUT codecs they depend on the incoming table)
-    Seg mine = segsum_identity<K>();
-    for (uint32_t s = lo; s < hi; s++)
-    {
-      Seg e; e.cs = B.scSum[s]; if (K) e.agg = B.scAgg[s]; else e.agg.m = 0; e.bytes = 0; e.ntok = B.scTok[s];
-      mine = segsum_combine<K>(mine, e);
-    }
-    Seg total;
-    const Seg pre = block_excl_scan(S, mine, total);
-    // (2) verification; a LUT super-chunk whose decisions did not depend on the incoming table only takes the exact table
-    AutoState st; Lut lut; enc_stream_incoming(B, W, st, lut);
-    segsum_apply<K>(st, lut, pre);
+    // (1) states: scan of the summaries (token bytes follow later: for LUT codecs they depend on the incoming table)
+    Seg mine = segsum_identity<K, AggR>();
+    for (uint32_t s = lo; s < hi; s++) mine = segsum_combine(mine, load_seg(B, s, 0));
+    const Seg pre = block_excl_scan(S, mine, total);              // (barriers inside: the resets above are visible)
+    // (2) a LUT super-chunk whose decisions did not depend on the incoming table only takes the exact table
+    AutoState st; LutR lut; enc_stream_incoming(B, W, st, lut);
+    segsum_apply(st, lut, pre);
     uint32_t nd = 0, first = 0xFFFFFFFFu;
     for (uint32_t s = lo; s < hi; s++)
     {
       bool bad = false;
       if (B.scIn[s] != st) { B.scIn[s] = st; bad = true; }
-      if (K && !lut_equal(B.scLut[s], lut, K)) { B.scLut[s] = lut; if (lut_sensitive(B, s, lut)) bad = true; }
+      if (K)
+      {
+        LutR cur; lut_from(cur, B.scLut[s]);
+        if (!lut_equal(cur, lut, K)) { lut_to(B.scLut[s], lut); if (lut_sensitive(B, s, lut)) bad = true; }
+      }
       B.scDirty[s] = bad ? 1 : 0;
-      if (bad) { if (!nd) first = s; nd++; }
-      chunksum_apply(st, B.scSum[s]);
-      if (K) lut_apply(lut, K, B.scAgg[s]);
+      if (bad)
+      {
+        if (!nd) first = s;
+        nd++;
+        const uint32_t slot = atomicAdd(&S.nList, 1u);
+        if (slot < (uint32_t)FIX_LIST) S.list[slot] = s;
+      }
+      const Seg e = load_seg(B, s, 0);
+      chunksum_apply(st, e.cs);
+      if (K) lut_apply(lut, K, e.agg);
     }
-    if (nd) { atomicAdd(&sDirty, nd); atomicMin(&sFirst, first); }
+    if (nd) { atomicAdd(&S.nDirty, nd); atomicMin(&S.firstDirty, first); }
     __syncthreads();
-    const uint32_t nDirty = sDirty, firstDirty = sFirst;
-    if (t == 0) { sc.nDirty[round] = nDirty; sc.firstDirty[round] = firstDirty; }
-    if (nDirty != 0 && round < enc_rounds(W, K) - 1) return;          // another round follows: offsets are not needed yet
-    // (3) token byte offsets (scLut[s] now is the exact incoming table of every super-chunk): per-thread sums, scan
+    return S.nDirty;
+  }
+
+  // ---- token byte offsets of the super-chunks (scLut[s] is the exact incoming table of every super-chunk), then either the
+  //      finish (nothing dirty) or the exact sequential repair from the first inconsistent super-chunk
+  static __device__ void offsets_and_finish(const EncBufs &B, FixSmem &S, const Seg &total, uint32_t nDirty)
+  {
+    EncScalars &sc = *B.sc;
+    const uint32_t nSC = sc.nSC;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t per = (nSC + FIX_T - 1) / FIX_T;
+    const uint32_t lo = min(nSC, (uint32_t)t * per), hi = min(nSC, lo + per);
     uint64_t bytes = 0;
     for (uint32_t s = lo; s < hi; s++)
     {
       B.scBase[s] = bytes;                       // relative to the thread's first super-chunk
-      Lut li; if (K) li = B.scLut[s]; else lut_init(li, W);
+      LutR li; if (K) lut_from(li, B.scLut[s]); else lut_init(li, W);
       bytes += sc_bytes(B, s, li);
     }
     uint64_t incB = bytes;
@@ -632,20 +668,21 @@ template <int W, int BA, int V, class SymT> struct EncCta
     if (lane == 31) S.warpBytes[warp] = incB;
     __syncthreads();
     uint64_t preB = incB - bytes, totalBytes = 0;
-#pragma unroll
-    for (int w = 0; w < E2_T / 32; w++) { const uint64_t x = S.warpBytes[w]; if (w < warp) preB += x; totalBytes += x; }
+#pragma unroll 1
+    for (int w = 0; w < FIX_W; w++) { const uint64_t x = S.warpBytes[w]; if (w < warp) preB += x; totalBytes += x; }
     for (uint32_t s = lo; s < hi; s++) B.scBase[s] += preB;
     __syncthreads();
-    AutoState fin; Lut finLut; enc_stream_incoming(B, W, fin, finLut);
-    segsum_apply<K>(fin, finLut, total);
+    AutoState fin; LutR finLut; enc_stream_incoming(B, W, fin, finLut);
+    segsum_apply(fin, finLut, total);
     if (nDirty == 0) { finish(B, fin, finLut, totalBytes, total.ntok); return; }
 
-    // exact repair after the last round: walk the super-chunks from the first inconsistent one with the exact
-    // running state; only those whose assumed incoming state is wrong are re-evaluated (one CTA / one warp each)
+    // exact repair: walk the super-chunks from the first inconsistent one with the exact running state; only those whose
+    // assumed incoming state is wrong are re-evaluated (one warp each, one after the other)
+    const uint32_t firstDirty = S.firstDirty;
     __threadfence();
-    if (t == 0) { S.bcSt = B.scIn[firstDirty]; if (K) S.bcLut = B.scLut[firstDirty]; }
+    if (t == 0) { S.bcSt = B.scIn[firstDirty]; if (K) lut_from(S.bcLut, B.scLut[firstDirty]); }
     __syncthreads();
-    AutoState run = S.bcSt; Lut runLut; if (K) runLut = S.bcLut; else lut_init(runLut, W);
+    AutoState run = S.bcSt; LutR runLut; if (K) runLut = S.bcLut; else lut_init(runLut, W);
     uint64_t runBytes = B.scBase[firstDirty];
     uint32_t runTok = 0;
     for (uint32_t s = 0; s < firstDirty; s++) runTok += B.scTok[s];   // small, uniform across threads
@@ -653,23 +690,24 @@ template <int W, int BA, int V, class SymT> struct EncCta
     {
       Seg tot;
       bool need = B.scDirty[s] != 0 || B.scIn[s] != run;               // uniform: every thread reads the same words
-      const bool lutDiff = K && !lut_equal(B.scLut[s], runLut, K);
+      bool lutDiff = false;
+      if (K) { LutR cur; lut_from(cur, B.scLut[s]); lutDiff = !lut_equal(cur, runLut, K); }
       if (lutDiff && lut_sensitive(B, s, runLut)) need = true;
       __syncthreads();
       if (need)
       {
-        if (warp == 0) { process(B, S, s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
+        if (warp == 0) { process(B, S.r[0], s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
         __syncthreads();
         tot = S.bcTot;
-        if (t == 0) { B.scIn[s] = run; if (K) B.scLut[s] = runLut; B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
+        if (t == 0) { B.scIn[s] = run; if (K) lut_to(B.scLut[s], runLut); B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
       }
       else
       {
-        tot.cs = B.scSum[s]; if (K) tot.agg = B.scAgg[s]; else tot.agg.m = 0; tot.bytes = sc_bytes(B, s, runLut); tot.ntok = B.scTok[s];
-        if (t == 0 && lutDiff) B.scLut[s] = runLut;
+        tot = load_seg(B, s, sc_bytes(B, s, runLut));
+        if (t == 0 && lutDiff) lut_to(B.scLut[s], runLut);
       }
       if (t == 0) B.scBase[s] = runBytes;
-      segsum_apply<K>(run, runLut, tot);
+      segsum_apply(run, runLut, tot);
       runBytes += tot.bytes; runTok += tot.ntok;
     }
     __syncthreads();
@@ -677,38 +715,159 @@ template <int W, int BA, int V, class SymT> struct EncCta
   }
 };
 
+// round 0: every super-chunk evaluated from a warmed-up state guess, one super-chunk per warp
 template <int W, int BA, int V, class SymT>
-__global__ void __launch_bounds__(E2_T, ((V == V_LUT3 || V == V_LUT7) && W > 1) ? 4 : 1) k_enc_auto(const EncBufs B, int round)
+__global__ void __launch_bounds__(E2_T, ((V == V_LUT3 || V == V_LUT7) && W > 1) ? 4 : 1) k_enc_auto(const EncBufs B)
 {
   using C = EncCta<W, BA, V, SymT>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   typename C::Smem &S = *reinterpret_cast<typename C::Smem *>(smemRaw);
-  EncScalars &sc = *B.sc;
-  if (round > 0 && sc.nDirty[round - 1] == 0) return;
-  const uint32_t nSC = sc.nSC;
-  constexpr int SCS_PER_CTA = C::NW;                                   // one super-chunk per warp
+  const uint32_t nSC = B.sc->nSC;
+  constexpr int SCS_PER_CTA = C::NW;
   const uint32_t sFirst = blockIdx.x * SCS_PER_CTA + (threadIdx.x >> 5);
   for (uint32_t s = sFirst; s < nSC; s += gridDim.x * SCS_PER_CTA)
   {
     typename C::Seg tot;
-    if (round == 0) { AutoState d = enc_initial_state(); Lut dl; lut_init(dl, W); C::process(B, S, s, false, d, dl, tot); }
-    else if (B.scDirty[s])
-    {
-      AutoState g = B.scIn[s]; Lut gl; if (C::K) gl = B.scLut[s]; else lut_init(gl, W);
-      C::process(B, S, s, true, g, gl, tot);
-    }
+    AutoState d = enc_initial_state(); typename C::LutR dl; lut_init(dl, W);
+    C::process(B, S.r[threadIdx.x >> 5], s, false, d, dl, tot);
   }
-  // the last CTA to get here scans and verifies
-  __syncthreads();
-  if (threadIdx.x == 0)
+}
+
+// verify / repair rounds inside ONE launch (no launch or grid-wide barrier per round).  CTA 0 is the master: verify scan over the
+// super-chunk summaries -> dirty super-chunks re-run from their exact incoming state -> verify again ... until nothing is dirty
+// (then offsets + finish) or the round budget is spent (then the exact sequential repair).  A round with few dirty super-chunks
+// is run by the master's 16 warps alone; a round with many is dealt out in tickets of FIX_BLK super-chunks that every resident
+// warp of the grid takes (the other CTAs only help: completion is counted per ticket, never per CTA, so nothing waits for a CTA
+// that is not resident -- safe with plain launches on concurrent streams).  The helpers leave as soon as the master sees a
+// round that it can run alone.  startDirty: the caller marked the dirty super-chunks itself (slices: the true incoming state of
+// the slice arrived).
+constexpr uint32_t FIX_BLK = 32;            // super-chunks per ticket
+constexpr uint32_t FIX_SOLO = 48;           // at most this many dirty super-chunks: the master runs the round alone
+
+template <int W, int BA, int V, class SymT>
+__device__ __forceinline__ void enc_fix_tickets(const EncBufs &B, typename EncCta<W, BA, V, SymT>::WarpRecs &R, uint32_t nSC)
+{ // warp-level: take tickets of the current round until none is left
+  using C = EncCta<W, BA, V, SymT>;
+  EncScalars &sc = *B.sc;
+  const int lane = threadIdx.x & 31;
+  const uint32_t nTickets = (nSC + FIX_BLK - 1) / FIX_BLK;
+  for (;;)
   {
-    __threadfence();
-    S.flag = (atomicAdd(&sc.done[round], 1u) == gridDim.x - 1) ? 1u : 0u;
+    uint32_t k = 0;
+    if (lane == 0) k = atomicAdd(&sc.fixTicket, 1u);
+    k = __shfl_sync(0xFFFFFFFFu, k, 0);
+    if (k >= nTickets) break;
+    const uint32_t s0 = k * FIX_BLK, s1 = min(nSC, s0 + FIX_BLK);
+    for (uint32_t s = s0; s < s1; s++)
+    {
+      if (!__ldcg(B.scDirty + s)) continue;
+      AutoState g; typename C::LutR gl;
+      { // written by the master in this launch: read through L2
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(&B.scIn[s]); uint32_t *q = reinterpret_cast<uint32_t *>(&g);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(AutoState) / 4); i++) q[i] = __ldcg(p + i);
+        if (C::K)
+        {
+          Lut tmp; const uint32_t *pl = reinterpret_cast<const uint32_t *>(&B.scLut[s]); uint32_t *ql = reinterpret_cast<uint32_t *>(&tmp);
+#pragma unroll
+          for (int i = 0; i < (int)(sizeof(Lut) / 4); i++) ql[i] = __ldcg(pl + i);
+          lut_from(gl, tmp);
+        }
+        else lut_init(gl, W);
+      }
+      typename C::Seg tot;
+      C::process(B, R, s, true, g, gl, tot);
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence(); atomicAdd(&sc.fixDone, 1u); }
   }
-  __syncthreads();
-  if (!S.flag) return;
-  __threadfence();
-  C::scan_verify(B, S, round);
+}
+
+template <int W, int BA, int V, class SymT>
+__global__ void __launch_bounds__(FIX_T, 1) k_enc_fix(const EncBufs B, int startDirty, int maxRounds)
+{
+  using C = EncCta<W, BA, V, SymT>;
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  typename C::FixSmem &S = *reinterpret_cast<typename C::FixSmem *>(smemRaw);
+  EncScalars &sc = *B.sc;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (blockIdx.x != 0)
+  { // helper CTA: wait for grid rounds, leave when told
+    uint32_t seen = 0;
+    for (;;)
+    {
+      uint32_t cmd = 0, rnd = 0;
+      if (lane == 0) { cmd = ld_volatile_u32g(&sc.fixCmd); rnd = ld_volatile_u32g(&sc.fixRound); }
+      cmd = __shfl_sync(0xFFFFFFFFu, cmd, 0); rnd = __shfl_sync(0xFFFFFFFFu, rnd, 0);
+      if (cmd) break;
+      if (rnd != seen) { seen = rnd; __threadfence(); enc_fix_tickets<W, BA, V, SymT>(B, S.r[warp], ld_volatile_u32g(&sc.nSC)); }
+      else __nanosleep(200);
+    }
+    return;
+  }
+  const uint32_t nSC = sc.nSC;
+  typename C::Seg total;
+  uint32_t nDirty = 0;
+  int round = 0;
+  bool helpers = gridDim.x > 1;
+  if (startDirty)
+  { // dirty marks come from the caller: count them (the list is rebuilt by the flags path below)
+    if (t == 0) { S.nList = 0; S.nDirty = 0; S.firstDirty = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (uint32_t s = t; s < nSC; s += FIX_T)
+      if (B.scDirty[s]) { atomicAdd(&S.nDirty, 1u); const uint32_t slot = atomicAdd(&S.nList, 1u); if (slot < (uint32_t)FIX_LIST) S.list[slot] = s; }
+    __syncthreads();
+    nDirty = S.nDirty;
+    if (nDirty == 0) nDirty = C::verify(B, S, total);
+  }
+  else nDirty = C::verify(B, S, total);
+  if (t == 0) sc.nDirty[0] = nDirty;
+  while (nDirty != 0 && round < maxRounds)
+  {
+    if (helpers && nDirty <= FIX_SOLO)
+    { // from here on the master runs alone: release the helpers
+      if (t == 0) { __threadfence(); st_volatile_u32g(&sc.fixCmd, 1u); }
+      helpers = false;
+    }
+    if (helpers)
+    { // grid round: states and dirty flags are in global memory; publish the round, take tickets, wait for all tickets
+      __syncthreads();
+      if (t == 0) { sc.fixTicket = 0; sc.fixDone = 0; __threadfence(); st_volatile_u32g(&sc.fixRound, (uint32_t)round + 1u); }
+      __syncthreads();
+      enc_fix_tickets<W, BA, V, SymT>(B, S.r[warp], nSC);
+      if (t == 0)
+      {
+        const uint32_t nTickets = (nSC + FIX_BLK - 1) / FIX_BLK;
+        while (ld_volatile_u32g(&sc.fixDone) < nTickets) __nanosleep(100);
+      }
+      __syncthreads();
+      __threadfence();                                  // helpers on other SMs rewrote summaries: nothing stale may be read from this SM's L1
+    }
+    else
+    { // solo round: one dirty super-chunk per warp.  (Following a changed outgoing state through the next super-chunks inside
+      // the round was measured twice -- r01 with claims, r02 without: rounds drop from 58 / 90 to 3 / 14 for rle8_3symlut /
+      // rle8_7symlut on the DCT stream, but the time does not (4.2 ms) or triples (33 ms): the cost is the one-warp re-run of
+      // a super-chunk, ~70 us, and followers re-run super-chunks a later verify invalidates again.)
+      const uint32_t nl = min(S.nList, (uint32_t)FIX_LIST);
+      const bool listed = S.nList <= (uint32_t)FIX_LIST;
+      __syncthreads();
+      for (uint32_t i = warp; i < (listed ? nl : nSC); i += FIX_W)
+      {
+        const uint32_t s = listed ? S.list[i] : i;
+        if (!listed && !B.scDirty[s]) continue;
+        AutoState g = B.scIn[s]; typename C::LutR gl; if (C::K) lut_from(gl, B.scLut[s]); else lut_init(gl, W);
+        typename C::Seg tot;
+        C::process(B, S.r[warp], s, true, g, gl, tot);
+      }
+      __threadfence_block();
+      __syncthreads();
+    }
+    round++;
+    nDirty = C::verify(B, S, total);
+  }
+  if (helpers && t == 0) { __threadfence(); st_volatile_u32g(&sc.fixCmd, 1u); }
+  if (t == 0) { sc.nDirty[1] = (uint32_t)round; sc.nDirty[2] = nDirty; }
+  C::offsets_and_finish(B, S, total, nDirty);
 }
 
 // ================================================================================================
@@ -798,23 +957,25 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     __syncthreads();
     const int j0 = E2_CH + t * E2_CH, j1 = min(j0 + E2_CH, E2_CH + (int)cnt);
     const bool active = j0 < j1;
-    AutoState st0 = enc_initial_state(); Lut lut0; lut_init(lut0, W);
+    using LutR = typename C::LutR;
+    using AggR = typename C::AggR;
+    AutoState st0 = enc_initial_state(); LutR lut0; lut_init(lut0, W);
     if (active)
     {
       st0 = B.cIn[s * E2_T + t];
-      if (K) { lut0 = B.cLut[s * E2_T + t]; enc_chunk_lut(lut0, B.cKnown[s * E2_T + t], K, B.scLut[s]); }
+      if (K) { Lut g0 = B.cLut[s * E2_T + t]; enc_chunk_lut(g0, B.cKnown[s * E2_T + t], K, B.scLut[s]); lut_from(lut0, g0); }
     }
     // pass 1: bytes of my chunk
     unsigned long long mine = 0;
     if (active)
     {
-      AutoState st = st0; Lut lut = lut0; LutAgg dummy; dummy.m = 0;
+      AutoState st = st0; LutR lut = lut0;
       for (int j = j0; j < j1; j++)
       {
         const int q = rec_slot(j);
         uint32_t rs, re; CountSink h;
         const uint32_t lastBefore = st.last;
-        const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &dummy : nullptr, rs, re, h);
+        const uint32_t ev = enc_eval_t<CountSink, LutR, AggR>(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, (AggR *)nullptr, rs, re, h);
         if (ev & EV_EMIT) mine += h.len + slice_lit_len(lastBefore, rs, floor);
       }
     }
@@ -833,14 +994,14 @@ __global__ void __launch_bounds__(E2_T) k_enc_emit(const EncBufs B)
     // pass 2: headers, literal descriptors
     if (active)
     {
-      AutoState st = st0; Lut lut = lut0; LutAgg dummy; dummy.m = 0;
+      AutoState st = st0; LutR lut = lut0;
       for (int j = j0; j < j1; j++)
       {
         const int q = rec_slot(j);
         uint32_t rs, re; PtrSink h;
         h.p = staged ? (S.stage + shift + (uint32_t)(pos - seg0)) : (out + pos);
         const uint32_t lastBefore = st.last;
-        const uint32_t ev = enc_eval(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, K ? &dummy : nullptr, rs, re, h);
+        const uint32_t ev = enc_eval_t<PtrSink, LutR, AggR>(sp, (uint64_t)S.sym[q], n, S.a[q], S.b[q], st, lut, (AggR *)nullptr, rs, re, h);
         if (!(ev & EV_EMIT)) continue;
         const uint32_t lit = slice_lit_len(lastBefore, rs, floor), litSrc = slice_lit_src(lastBefore, floor);
         if (B.sliceMode && pos == B.outBase)
