@@ -7,6 +7,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <time.h>
+#include <unistd.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -171,25 +174,22 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
 {
   Carver cv{ (uint8_t *)ws, 0 };
   D.inSize = inSize; D.outSize = outSize;
-  D.nSC = (uint32_t)(((uint64_t)inSize + DEC_SCB - 1) / DEC_SCB);
-  D.nSeg = (D.nSC + DEC_SEG - 1) / DEC_SEG;
+  D.nChunks = (uint32_t)(((uint64_t)inSize + DEC_CB - 1) / DEC_CB);
+  D.nSeg = (D.nChunks + DEC_SEG - 1) / DEC_SEG;
   const size_t aggBytes = sp.K ? sizeof(DecAgg<7>) : sizeof(DecAgg<0>);
   // zero-initialised region first
-  D.sc = cv.take<DecScalars>(1);
-  D.flagAgg = cv.take<uint32_t>((size_t)D.nSC + 1); D.flagInc = cv.take<uint32_t>((size_t)D.nSC + 1);
-  D.flagSeg = cv.take<uint32_t>((size_t)D.nSeg + 1); D.chainFlag = cv.take<uint32_t>((size_t)D.nSeg + 1);
-  D.scSkip = cv.take<uint32_t>((size_t)D.nSC + 1);
-  D.sufExit = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);          // zeroed: 0 = "row not published yet"
+  D.cnt = cv.take<DecCounters>(1);
+  D.segCount = cv.take<uint32_t>((size_t)D.nSeg + 1);
+  D.anchorAt = cv.take<uint32_t>((size_t)D.nChunks + 1);
+  D.flagAgg = cv.take<uint32_t>((size_t)D.nChunks + 1);
+  D.bigCap = (uint32_t)(((size_t)outSize / ((size_t)DEC_TILE * DEC_HUGE_TILES)) + 64);      // every such operation covers at least 256 KiB of output
+  D.bigList = cv.take<DecBigOp>(D.bigCap);                                                  // (their `ready` words must start as 0)
   if (zeroBytes) *zeroBytes = cv.off;
-  D.chainPos = cv.take<uint32_t>((size_t)D.nSeg + 1);
-  D.medList = cv.take<DecBigOp>(((size_t)outSize >> 12) + 16);       // every deferred operation covers more than 4 KiB of output
-  D.hugeList = cv.take<DecBigOp>(((size_t)outSize >> 18) + 16);
-  D.exTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
-  D.scTab = cv.take<uint16_t>((size_t)D.nSC * DEC_SCB);
-  D.farTab = cv.take<uint32_t>((size_t)D.nSC * DEC_SCB);
-  D.winTab = cv.take<uint32_t>((size_t)D.nSC * DEC_WIN);
-  D.scEntry = cv.take<uint32_t>(D.nSC + 1);
-  D.aggBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nSC + 1) * aggBytes);
+  D.sc = cv.take<DecScalars>(1);
+  D.chunkMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WIN);
+  D.sufMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WIN);
+  D.subMap = cv.take<uint16_t>((size_t)D.nChunks * DEC_NSUB * DEC_WIN);
+  D.aggBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes);
   return cv.off + 256;
 }
 
@@ -322,23 +322,20 @@ static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
 
 static std::mutex g_dattrMu;
 static bool g_dattrDone[MAX_DEV][48];
-static bool g_composeAttr[MAX_DEV];
+static int g_emitGrid[MAX_DEV][48];
 static bool dec_prepare(int codec, const DecKernels *k)
 {
   const int dev = current_dev();
   std::lock_guard<std::mutex> lk(g_dattrMu);
-  if (!g_composeAttr[dev])
-  {
-    if (!cuda_ok(cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem)), "attr chain")) return false;
-    g_composeAttr[dev] = true;
-  }
   if (g_dattrDone[dev][codec]) return true;
   cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute((const void *)k->big, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute((const void *)k_dec_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->mapSmem), "attr map")) return false;
   if (!cuda_ok(cudaFuncSetAttribute((const void *)k->emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->emitSmem), "attr emit")) return false;
+  // the emit kernel is persistent: as many CTAs as fit the device at once
+  int perSM = 0;
+  if (!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, (const void *)k->emit, DX_T, k->emitSmem), "occupancy emit")) return false;
+  g_emitGrid[dev][codec] = std::max(1, perSM) * num_sms();
   g_dattrDone[dev][codec] = true;
   return true;
 }
@@ -356,11 +353,33 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   const size_t need = dec_carve(D, sp, inSize, outSize, ws, &zeroBytes);
   if (need > wsSize) { g_err = "workspace too small"; return 1; }
   D.in = dIn; D.out = dOut; D.dResult = dResult;
+  D.emitGrid = (uint32_t)g_emitGrid[current_dev()][codec];
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
-  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nSC, DM_T, k->mapSmem, st, D);
-  HSRLE_LAUNCH(k_dec_chain, D.nSeg, DC_T, sizeof(DecChainSmem), st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_emit", k->emit, D.nSC, DX_T, k->emitSmem, st, D);
-  HSRLE_LAUNCH_NAMED("k_dec_big", k->big, num_sms() * 4, 256, 0, st, D);
+  static const bool dbg = getenv("HSRLE_DEBUG") != nullptr;
+  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nChunks, DM_T, k->mapSmem, st, D);
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[hsrle] k_dec_map done: %s (chunks %u)\n", cudaGetErrorString(e), D.nChunks); fflush(stderr); }
+  static uint32_t *hDbg = nullptr;
+  if (dbg)
+  {
+    if (!hDbg) cudaHostAlloc((void **)&hDbg, 4096 * 4, cudaHostAllocMapped);
+    memset(hDbg, 0, 4096 * 4);
+    cudaHostGetDevicePointer((void **)&D.dbg, hDbg, 0);
+  }
+  HSRLE_LAUNCH_NAMED("k_dec_emit", k->emit, D.emitGrid, DX_T, k->emitSmem, st, D);
+  if (dbg)
+  {
+    for (int ms = 0; ms < 8000 && cudaStreamQuery(st) == cudaErrorNotReady; ms += 50) { struct timespec ts = { 0, 50000000 }; nanosleep(&ts, nullptr); }
+    if (cudaStreamQuery(st) == cudaErrorNotReady)
+    {
+      fprintf(stderr, "[hsrle] k_dec_emit STUCK (grid %u); stage markers of the CTAs (stage<<24 | arg), zeros omitted:\n", D.emitGrid);
+      std::map<uint32_t, int> hist;
+      for (uint32_t b = 0; b < D.emitGrid && b < 4096; b++) { hist[hDbg[b] >> 24]++; if ((hDbg[b] >> 24) != 0xA && hDbg[b]) fprintf(stderr, "  cta %u: %08x\n", b, hDbg[b]); }
+      for (auto &kv : hist) fprintf(stderr, "  stage %x: %d CTAs\n", kv.first, kv.second);
+      fflush(stderr);
+      _exit(3);
+    }
+    fprintf(stderr, "[hsrle] k_dec_emit done: %s (grid %u)\n", cudaGetErrorString(cudaStreamSynchronize(st)), D.emitGrid); fflush(stderr);
+  }
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }
 

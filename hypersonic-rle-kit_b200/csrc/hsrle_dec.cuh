@@ -198,6 +198,7 @@ struct DecBufs
   DecBigOp *bigList;
   uint32_t bigCap;
   uint32_t *dResult;
+  uint32_t *dbg;            // debugging aid (HSRLE_DEBUG): host-mapped stage markers, one word per CTA of K2; null otherwise
 };
 
 // header check -- src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91 (every CTA evaluates it itself)

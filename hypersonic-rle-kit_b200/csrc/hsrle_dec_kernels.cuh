@@ -7,49 +7,45 @@
 namespace hsrle {
 
 // ================================================================================================
-// shared-memory image of an SC.  One thread owns one 128-byte mini-block, so byte and table addresses are
-// skewed by one word per mini-block: lane t then starts at bank t instead of bank 0 (no 32-way conflicts).
-__device__ __forceinline__ uint32_t skew8(uint32_t x) { return x + ((x >> 7) << 2); }     // byte index
-__device__ __forceinline__ uint32_t skew16(uint32_t x) { return x + ((x >> 7) << 1); }    // u16 index
-constexpr uint32_t DEC_DATA_BYTES = DEC_SCB + DEC_PAD + ((DEC_SCB + DEC_PAD) / 128 + 1) * 4;
-constexpr uint32_t DEC_EX_ELEMS = DEC_SCB + (DEC_SCB / 128 + 1) * 2;
+// small device utilities
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return ld_volatile_u32g(p); }
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) { st_volatile_u32g(p, v); }
 
-struct SkewReader
+// ---- 1-D bulk copies (TMA) global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
-  const uint8_t *data; uint32_t p;
-  __device__ __forceinline__ uint32_t u8(uint32_t o) const { return data[skew8(p + o)]; }
-};
-
-// load stream bytes [c0, c0 + DEC_SCB + DEC_PAD) (zero beyond clen) into the skewed image -- 16-byte coalesced
-__device__ __forceinline__ void dec_load_sc(uint8_t *data, const uint8_t *__restrict__ in, uint32_t c0, uint32_t clen)
-{
-  constexpr int NV = (DEC_SCB + DEC_PAD) / 16;
-  const uint4 *src = reinterpret_cast<const uint4 *>(in + c0);
-  const uint32_t avail = clen > c0 ? clen - c0 : 0;
-  for (int v = threadIdx.x; v < NV; v += blockDim.x)
-  {
-    const uint32_t b = (uint32_t)v * 16;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (b < avail) x = __ldg(src + v);     // the 16-byte block holding byte clen-1 lies inside the caller's allocation
-    uint32_t w[4] = { x.x, x.y, x.z, x.w };
-    if (b + 16 > avail)
-    { // zero the bytes at and beyond clen so that nothing depends on them
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-      {
-        const uint32_t bb = b + 4 * k;
-        if (bb >= avail) w[k] = 0;
-        else if (bb + 4 > avail) w[k] &= (1u << (8 * (avail - bb))) - 1u;
-      }
-    }
-    uint32_t *dst = reinterpret_cast<uint32_t *>(data + skew8(b));
-    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2]; dst[3] = w[3];
-  }
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// (bounded: a copy that never lands -- it cannot, with the sizes and alignments used here -- must not hang the device; the
+//  caller records the failure and the call returns 0)
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok && spin < (1u << 22); spin++)
+  {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+  return ok != 0;
+}
+// generic-proxy accesses to shared memory before this point are ordered before later async-proxy (bulk copy) accesses
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// length-only token parse from a 24-byte register window (bytes p .. p+23 of the stream).  Same decisions
-// as dec_parse (hsrle_core.cuh), restricted to what the chain needs: kind and the distance to the next token.
+// token parse from a 24-byte register window (bytes p .. p+23 of the stream).  Same decisions as dec_parse
+// (hsrle_core.cuh), branch free.
 struct TokWin { uint32_t w[6]; };
 template <int K> __device__ __forceinline__ uint32_t win_u8(const TokWin &x) { return (x.w[K >> 2] >> (8 * (K & 3))) & 0xFFu; }
 template <int K> __device__ __forceinline__ uint32_t win_u32(const TokWin &x)
@@ -58,9 +54,11 @@ template <int K> __device__ __forceinline__ uint32_t win_u32(const TokWin &x)
   else return __funnelshift_r(x.w[K >> 2], x.w[(K >> 2) + 1], 8 * (K & 3));
 }
 enum : uint32_t { TK_OK = 0, TK_END = 1, TK_BAD = 2 };
+// what K2 needs beyond the length: header bytes, stored count, where the explicit symbol sits (0xFF: none), LUT index
+struct TokF { uint32_t hdr, cnt, symOff, idx; };
 
 // [S symbol bytes][cnt][rng] with 8-bit fields and 0-escapes (plain tokens; S = 0 for single-symbol streams)
-template <int S> __device__ __forceinline__ uint32_t toklen_plain(const TokWin &x, uint32_t avail, uint32_t &kind)
+template <int S> __device__ __forceinline__ uint32_t toklen_plain(const TokWin &x, uint32_t avail, uint32_t &kind, TokF &f)
 {
   const uint32_t c = win_u8<S>(x);
   const bool e1 = c == 0;
@@ -72,10 +70,11 @@ template <int S> __device__ __forceinline__ uint32_t toklen_plain(const TokWin &
   const uint32_t rng = e2 ? r32 : r;
   // (a token fits iff hdr <= avail and rng - 1 <= avail - hdr: no 64-bit arithmetic; len is only used when it fits)
   kind = (hdr > avail) ? TK_BAD : (rng == 0) ? TK_END : (rng - 1 > avail - hdr) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
+  f.hdr = hdr; f.cnt = e1 ? cnt32 : c; f.symOff = S ? 0u : 0xFFu; f.idx = 0;
   return hdr + rng - 1;
 }
 // packed tokens: b0 = same<<7 | cnt7, optional u32 cnt, optional symbol, rng in the 7-bit or the 8-bit style
-template <int W, bool RNG7> __device__ __forceinline__ uint32_t toklen_packed(const TokWin &x, uint32_t avail, uint32_t &kind)
+template <int W, bool RNG7> __device__ __forceinline__ uint32_t toklen_packed(const TokWin &x, uint32_t avail, uint32_t &kind, TokF &f)
 {
   const uint32_t b0 = win_u8<0>(x);
   const bool e1 = (b0 & 0x7F) == 0, same = (b0 & 0x80) != 0;
@@ -100,14 +99,16 @@ template <int W, bool RNG7> __device__ __forceinline__ uint32_t toklen_packed(co
     endMark = esc && rng == 0;
   }
   kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng == 0 || rng - 1 > avail - hdr) ? TK_BAD : (e1 && cnt32 == 0) ? TK_END : TK_OK;
+  f.hdr = hdr; f.cnt = e1 ? cnt32 : (b0 & 0x7F); f.symOff = same ? 0xFFu : (e1 ? 5u : 1u); f.idx = 0;
   return hdr + rng - 1;
 }
 // LUT tokens: u16 head = idx | cnt7 | rng, optional symbol, optional u16/u32 cnt, optional u16/u32 rng
-template <int W, int K> __device__ __forceinline__ uint32_t toklen_lut(const TokWin &x, uint32_t avail, uint32_t &kind)
+template <int W, int K> __device__ __forceinline__ uint32_t toklen_lut(const TokWin &x, uint32_t avail, uint32_t &kind, TokF &f)
 {
   constexpr int RB = (K == 3) ? 7 : 6;
   const uint32_t head = win_u32<0>(x) & 0xFFFFu;
-  const bool miss = (head >> (K == 3 ? 14 : 13)) == (uint32_t)K;
+  const uint32_t idx = head >> (K == 3 ? 14 : 13);
+  const bool miss = idx == (uint32_t)K;
   const uint32_t c7 = (head >> RB) & 0x7F, r = head & ((1u << RB) - 1u);
   const uint32_t ce = c7 == 1 ? 2u : (c7 == 0 ? 4u : 0u);
   const uint32_t x1 = miss ? win_u32<2 + W>(x) : win_u32<2>(x);
@@ -119,89 +120,148 @@ template <int W, int K> __device__ __forceinline__ uint32_t toklen_lut(const Tok
   const uint32_t hdr = 2 + (miss ? (uint32_t)W : 0u) + ce + re;
   const bool endMark = r == 1 && rng == 0;
   kind = (hdr > avail) ? TK_BAD : endMark ? TK_END : (rng < 2 || rng - 2 > avail - hdr) ? TK_BAD : (cnt == 0) ? TK_END : TK_OK;
+  f.hdr = hdr; f.cnt = cnt; f.symOff = miss ? 2u : 0xFFu; f.idx = idx;
   return hdr + rng - 2;
 }
 template <int W, int BA, int V>
-__device__ __forceinline__ uint32_t toklen(const TokWin &x, bool single, uint32_t avail, uint32_t &kind)
+__device__ __forceinline__ uint32_t toklen(const TokWin &x, bool single, uint32_t avail, uint32_t &kind, TokF &f)
 {
   constexpr Spec sp = make_spec(W, BA, V);
-  if constexpr (sp.K != 0) return toklen_lut<W, sp.K>(x, avail, kind);
+  if constexpr (sp.K != 0) return toklen_lut<W, sp.K>(x, avail, kind, f);
   else
   {
-    if constexpr (W == 1) { if (single) return toklen_plain<0>(x, avail, kind); }
-    if constexpr (V == V_PLAIN) return toklen_plain<W>(x, avail, kind);
-    else return toklen_packed<W, sp.rng7 != 0>(x, avail, kind);
+    if constexpr (W == 1) { if (single) return toklen_plain<0>(x, avail, kind, f); }
+    if constexpr (V == V_PLAIN) return toklen_plain<W>(x, avail, kind, f);
+    else return toklen_packed<W, sp.rng7 != 0>(x, avail, kind, f);
+  }
+}
+// the token at byte p of a shared-memory stream image (p + 28 bytes readable)
+template <int W, int BA, int V>
+__device__ __forceinline__ uint32_t toklen_at(const uint8_t *img, uint32_t p, bool single, uint32_t avail, uint32_t &kind, TokF &f)
+{
+  const uint32_t *d32 = reinterpret_cast<const uint32_t *>(img) + (p >> 2);
+  const uint32_t sh = (p & 3u) * 8u;
+  uint32_t w[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) w[k] = d32[k];
+  TokWin x;
+#pragma unroll
+  for (int k = 0; k < 6; k++) x.w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+  return toklen<W, BA, V>(x, single, avail, kind, f);
+}
+// output bytes of the run part of a token with stored count c
+template <int W, int BA, int V> __device__ __forceinline__ uint32_t tok_run_bytes(uint32_t c, bool single)
+{
+  constexpr Spec sp = make_spec(W, BA, V);
+  if (c == 0) return 0;
+  if constexpr (sp.K != 0) return (W == 1 || sp.byteAlign) ? c + 1 : (c + 3 / W - 2) * W;
+  else
+  {
+    if (single) return c + (V == V_PLAIN ? 3 : 1);
+    return (W == 1 || sp.byteAlign) ? c + sp.SHORT - 1 : (c + sp.SHORT / W - 1) * W;
   }
 }
 
 // ================================================================================================
-// D1: per-position exit tables, one CTA per SC.
-//
-// ex[q] (u16, SC-relative code): < EX_FAR: where the chain that starts at q leaves q's mini-block (exTab, kept for D3) /
-// the SC (scTab, after the two-level in-place finalisation), a position of [c0, c0 + 0x8000); EX_END / EX_BAD;
-// EX_FARP | q': the chain reaches the token at q', which jumps beyond c0 + 0x7FFF and whose absolute exit is
-// farTab[c0 + q'].  D2 reads the table as codes and translates the few entries it needs; only the first DEC_WIN entries
-// of an SC (its windowed exit map, read by every call of D2) are also kept as absolute positions (winTab).
+// K1: k_dec_map -- windowed exit rows per chunk, segment composition, chain resolution (anchors)
 constexpr int DM_T = 256;
-constexpr int DM_SCOUT = 8;                // true-chain tokens the scout of D1 follows at most
-constexpr uint32_t DEC_HB = 64;             // half mini-block: the unit one thread sweeps
-constexpr uint32_t DEC_LIN_BYTES = DEC_SCB + 48;
+constexpr int DM_SCOUT = 8;                // true-chain tokens the scout follows at most
+constexpr uint32_t DEC_HB = 64;            // the unit one thread sweeps
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
-constexpr uint32_t DEC_EXH_ELEMS = DEC_SCB + (DEC_SCB / 64 + 1) * 2;
+constexpr uint32_t DEC_EXH_ELEMS = DEC_CB + (DEC_CB / 64 + 1) * 2;
+constexpr uint32_t DEC_IMG_BYTES = DEC_CB + DEC_IMG_PAD + 64;
+constexpr uint32_t DM_STAGE_ROWS = 40;     // segment rows the resolver stages at a time
 
-// The SC image is only read by phase A, which turns it into exit codes front to back, 1 KiB of stream (2112 bytes of
-// table) per step of the CTA: image and table share one buffer, the image at its far end, and a block barrier per step
-// keeps the table's write front below the image's read front (step it writes below 2112 (it + 1) and reads from
-// DM_DATA0 + 1024 it on: DM_DATA0 >= 1088 * 15 + 2112).  35 KB instead of 50 KB per CTA: 6 CTAs per SM instead of 4.
-constexpr uint32_t DM_DATA0 = 18560;
-static_assert(DM_DATA0 % 16 == 0 && DM_DATA0 >= 1088 * (DEC_SCB / 1024 - 1) + 2112, "image must stay ahead of the table");
 struct DecMapSmem
 {
-  alignas(16) uint8_t buf[DM_DATA0 + DEC_LIN_BYTES];
-  __device__ __forceinline__ uint8_t *data() { return buf + DM_DATA0; }                    // linear SC image (+ the longest token head after it)
-  __device__ __forceinline__ uint16_t *ex() { return reinterpret_cast<uint16_t *>(buf); }   // DEC_EXH_ELEMS entries
+  alignas(16) uint8_t img[DEC_IMG_BYTES];          // chunk image + pad (bulk-copy destination)
+  alignas(16) uint16_t ex[DEC_EXH_ELEMS];           // per-position exit codes (skewed)
+  alignas(8) unsigned long long mbar;
+  uint32_t flag, pos, gBase, done;
 };
-static_assert(DEC_EXH_ELEMS * 2 <= DM_DATA0 + DEC_LIN_BYTES, "table fits the buffer");
-constexpr uint32_t DEC_WB = 2048;            // warp-block: the 16 mini-blocks finalised by one warp
+static_assert(DEC_IMG_BYTES % 16 == 0 && DEC_IMG_BYTES + DEC_EXH_ELEMS * 2 >= DM_STAGE_ROWS * DEC_WIN * 4, "rows fit the image + table area");
+static_assert(DEC_SEG * DEC_WIN * 4 <= DEC_IMG_BYTES + DEC_EXH_ELEMS * 2, "segment rows fit");
 
-// load stream bytes [c0, c0 + DEC_LIN_BYTES) (zero beyond clen), linear -- 16-byte coalesced
-__device__ __forceinline__ void dec_load_sc_linear(uint8_t *data, const uint8_t *__restrict__ in, uint32_t c0, uint32_t clen)
-{
-  constexpr int NV = DEC_LIN_BYTES / 16;
-  const uint4 *src = reinterpret_cast<const uint4 *>(in + c0);
-  const uint32_t avail = clen > c0 ? clen - c0 : 0;
-  for (int v = threadIdx.x; v < NV; v += blockDim.x)
-  {
-    const uint32_t b = (uint32_t)v * 16;
-    uint4 x = make_uint4(0, 0, 0, 0);
-    if (b < avail) x = __ldg(src + v);     // the 16-byte block holding byte clen-1 lies inside the caller's allocation
-    uint32_t w[4] = { x.x, x.y, x.z, x.w };
-    if (b + 16 > avail)
-    { // zero the bytes at and beyond clen so that nothing depends on them
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-      {
-        const uint32_t bb = b + 4 * k;
-        if (bb >= avail) w[k] = 0;
-        else if (bb + 4 > avail) w[k] &= (1u << (8 * (avail - bb))) - 1u;
-      }
-    }
-    reinterpret_cast<uint4 *>(data)[v] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-// absolute position (or POS_END / POS_BAD) a final exit code of SC c stands for
-__device__ __forceinline__ uint32_t dec_code_pos(uint32_t code, uint32_t c0, const uint32_t *farRow)
+// absolute position (or POS_END / POS_BAD) a final exit code stands for; far-jumping tokens are parsed again from the image
+template <int W, int BA, int V>
+__device__ __forceinline__ uint32_t dec_code_abs(uint32_t code, uint32_t c0, const uint8_t *img, bool single, uint32_t availSC)
 {
   if (code < EX_FAR) return c0 + code;
   if (code < EX_FARP) return code == EX_END ? POS_END : POS_BAD;
-  return __ldcg(farRow + (code & 0x3FFFu));
+  const uint32_t p = code & 0x3FFFu;
+  uint32_t kind; TokF f;
+  const uint32_t len = toklen_at<W, BA, V>(img, p, single, availSC - p, kind, f);
+  return kind == TK_OK ? c0 + p + len : (kind == TK_END ? POS_END : POS_BAD);
 }
-// where the chain that starts at stream position x (< clen) leaves x's SC
-__device__ __forceinline__ uint32_t dec_sc_exit(const DecBufs &D, uint32_t x)
+
+// the resolver: follows the true chain from the stream start, leaves an anchor in every chunk it visits
+template <int W, int BA, int V>
+__device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &S, uint32_t *rows)
 {
-  const uint32_t c0 = (x / DEC_SCB) * DEC_SCB;
-  return dec_code_pos(__ldg(D.scTab + x), c0, D.farTab + (size_t)c0);
+  constexpr Spec sp = make_spec(W, BA, V);
+  const int t = threadIdx.x;
+  const uint32_t clen = hs.clen;
+  const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB, nSeg = (nChunks + DEC_SEG - 1) / DEC_SEG;
+  const bool single = hs.single != 0;
+  if (t == 0) { S.pos = hs.first; S.gBase = 0; S.done = 0; }
+  __syncthreads();
+  uint32_t lastAnchor = 0xFFFFFFFFu;
+  for (;;)
+  {
+    const uint32_t g0 = S.gBase;
+    // stage the rows of the first chunks of segments [g0, g0 + DM_STAGE_ROWS)
+    const uint32_t nr = min((uint32_t)DM_STAGE_ROWS, nSeg - g0);
+    for (uint32_t i = t; i < nr * DEC_WIN; i += DM_T)
+    {
+      const uint32_t g = g0 + i / DEC_WIN, w = i % DEC_WIN;
+      rows[i] = __ldcg(D.sufMap + (size_t)g * DEC_SEG * DEC_WIN + w);
+    }
+    __syncthreads();
+    if (t == 0)
+    {
+      uint32_t pos = S.pos;
+      bool fin = false;
+      for (uint32_t guard = 0;; guard++)
+      {
+        if (guard > (1u << 22)) { pos = POS_BAD; fin = true; D.cnt->chainBad = 0x600; break; }   // (every step advances by at least one token: never reached)
+        if (pos >= POS_SPECIAL) { fin = true; break; }
+        if (pos >= clen) { pos = POS_BAD; fin = true; break; }
+        const uint32_t c = pos / DEC_CB, o = pos - c * DEC_CB, g = c / DEC_SEG;
+        if (g >= g0 + nr) break;                                    // beyond the staged rows: stage again from there
+        if (c != lastAnchor) { D.anchorAt[c] = pos; lastAnchor = c; }
+        if (o < DEC_WIN)
+        {
+          if (c == g * DEC_SEG && g >= g0) pos = rows[(g - g0) * DEC_WIN + o];
+          else pos = __ldcg(D.sufMap + (size_t)c * DEC_WIN + o);
+        }
+        else
+        { // outside every chunk window (after a long literal): sub-chunk row if inside a sub-chunk window, else parse the token
+          const uint32_t s = o / DEC_SB, os = o - s * DEC_SB;
+          uint32_t tp = pos;                                         // position of the token to parse (if any)
+          bool parse = true;
+          if (os < DEC_WIN)
+          {
+            const uint32_t code = __ldcg(D.subMap + ((size_t)c * DEC_NSUB + s) * DEC_WIN + os);
+            if (code < EX_FAR) { pos = c * DEC_CB + code; parse = false; }
+            else if (code < EX_FARP) { pos = code == EX_END ? POS_END : POS_BAD; parse = false; }
+            else tp = c * DEC_CB + (code & 0x3FFFu);
+          }
+          if (parse)
+          {
+            Tok tk; dec_parse(sp, single, D.in + tp, (uint64_t)clen - tp, tk);
+            if (!tk.valid) pos = POS_BAD;
+            else if (tk.last) pos = POS_END;
+            else pos = tp + tk.hdrLen + tk.litLen;                   // <= clen (the token fits)
+          }
+        }
+      }
+      S.pos = pos;
+      if (fin) S.done = 1; else S.gBase = pos / DEC_CB / DEC_SEG;
+    }
+    __syncthreads();
+    if (S.done) break;
+  }
+  if (t == 0 && S.pos != POS_END) D.cnt->chainBad = 1;
 }
 
 template <int W, int BA, int V>
@@ -210,22 +270,32 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   constexpr Spec sp = make_spec(W, BA, V);
   extern __shared__ __align__(16) unsigned char smemRaw[];
   DecMapSmem &S = *reinterpret_cast<DecMapSmem *>(smemRaw);
+  uint32_t *const rows = reinterpret_cast<uint32_t *>(smemRaw);      // segment / resolver rows alias the image + table area
   DecScalars hs; dec_header(sp, D.in, D.inSize, D.outSize, hs);
   if (blockIdx.x == 0 && threadIdx.x == 0) *D.sc = hs;
   if (hs.status != ST_OK) return;
   const uint32_t c = blockIdx.x;
-  const uint32_t c0 = c * DEC_SCB;
+  const uint32_t c0 = c * DEC_CB;
   const uint32_t clen = hs.clen;
   if (c0 >= clen) return;
+  const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB, nSeg = (nChunks + DEC_SEG - 1) / DEC_SEG;
   const bool single = hs.single != 0;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  uint32_t *farRow = D.farTab + (size_t)c0;
-  // Scout: the first tokens of the TRUE chain can be followed from the stream start without any table as long as each
-  // of them jumps over whole SCs (incompressible input is one token with a literal of the whole input).  An SC such a
-  // token jumps over holds no token start: its tables only have to be safe for the speculative chains that land in it
-  // ("unparsable"), not computed.  The scout stops at the first ordinary token, i.e. after one parse on ordinary data.
+  const int t = threadIdx.x;
+  uint16_t *const ex = S.ex;
+  const uint32_t availSC = clen - c0;                                 // stream bytes from the start of the chunk
+  // ---- the chunk image: one bulk copy (rounded up to 16 bytes: the caller's buffer is readable up to the next 16-byte
+  //      boundary after the stream, include/hsrle_b200.h)
+  if (t == 0)
   {
-    __shared__ uint32_t sSkip;
+    mbar_init(&S.mbar, 1);
+    const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
+    mbar_expect_tx(&S.mbar, bytes);
+    bulk_load(S.img, D.in + c0, bytes, &S.mbar);
+  }
+  // Scout: the first tokens of the TRUE chain can be followed from the stream start without any table as long as each
+  // of them jumps over whole chunks (incompressible input is one token with a literal of the whole input).  A chunk such a
+  // token jumps over holds no token start: its rows only have to be safe for the speculative chains that land in it.
+  {
     if (t == 0)
     {
       uint32_t skip = 0, p = hs.first;
@@ -233,334 +303,190 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
       {
         Tok tk; dec_parse(sp, single, D.in + p, (uint64_t)clen - p, tk);
         if (!tk.valid) break;
-        if (tk.last) { skip = 1; break; }                             // the final token starts before this SC: nothing starts in it
+        if (tk.last) { skip = 1; break; }                             // the final token starts before this chunk: nothing starts in it
         const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
-        if (nx >= (uint64_t)c0 + DEC_SCB) { skip = 1; break; }        // starts before this SC, next token after it
-        if (tk.litLen < 4 * DEC_SCB) break;
+        if (nx >= (uint64_t)c0 + DEC_CB) { skip = 1; break; }         // starts before this chunk, next token after it
+        if (tk.litLen < 4 * DEC_CB) break;
         p = (uint32_t)nx;
       }
-      sSkip = skip;
+      S.flag = skip;
     }
-    __syncthreads();
-    if (sSkip)
-    {
-      const uint32_t bad2 = EX_BAD | (EX_BAD << 16);
-      uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
-      for (uint32_t q = t; q < DEC_SCB / 8; q += DM_T) dst[q] = make_uint4(bad2, bad2, bad2, bad2);
-      for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = POS_BAD;
-      if (t == 0) D.scSkip[c] = 1u;
-      return;
-    }
+    __syncthreads();                                                  // (also: mbarrier initialised before anybody waits)
   }
-  uint16_t *const ex = S.ex();
-  dec_load_sc_linear(S.data(), D.in, c0, clen);
+  const bool skipped = S.flag != 0;
+  if (!mbar_wait(&S.mbar, 0)) D.cnt->chainBad = 0x100;               // the copy must have landed before the area is reused
   __syncthreads();
-
-  // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
-  //      words give the four 24-byte windows); raw code = where that token ends
+  if (skipped)
   {
-    const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.data());
-    const uint32_t availSC = clen - c0;              // stream bytes from the start of the SC
-    for (int it = 0; it < (int)(DEC_SCB / (4 * DM_T)); it++)
+    for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.chunkMap[(size_t)c * DEC_WIN + w] = POS_BAD;
+  }
+  else
+  {
+    // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
+    //      words give the four 24-byte windows); raw code = where that token ends
     {
-      const uint32_t p4 = (uint32_t)(it * DM_T + t) * 4;
-      uint32_t w[7];
-#pragma unroll
-      for (int k = 0; k < 7; k++) w[k] = d32[(p4 >> 2) + k];
-      uint32_t codes[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++)
+      const uint32_t *d32 = reinterpret_cast<const uint32_t *>(S.img);
+#pragma unroll 2
+      for (int it = 0; it < (int)(DEC_CB / (4 * DM_T)); it++)
       {
-        TokWin x;
+        const uint32_t p4 = (uint32_t)(it * DM_T + t) * 4;
+        uint32_t w[7];
 #pragma unroll
-        for (int k = 0; k < 6; k++) x.w[k] = j ? __funnelshift_r(w[k], w[k + 1], 8 * j) : w[k];
-        const uint32_t p = p4 + j;
-        uint32_t kind;
-        const uint32_t len = toklen<W, BA, V>(x, single, p < availSC ? availSC - p : 0u, kind);
-        const uint32_t nr = p + len;                  // <= availSC when the token fits
-        uint32_t code = kind == TK_END ? EX_END : EX_BAD;
-        if (kind == TK_OK)
+        for (int k = 0; k < 7; k++) w[k] = d32[(p4 >> 2) + k];
+        uint32_t codes[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
         {
-          code = nr;
-          if (nr >= EX_FAR) { farRow[p] = c0 + nr; code = EX_FARP | p; }   // far jump: its absolute exit is parked in its own farTab entry
+          TokWin x;
+#pragma unroll
+          for (int k = 0; k < 6; k++) x.w[k] = j ? __funnelshift_r(w[k], w[k + 1], 8 * j) : w[k];
+          const uint32_t p = p4 + j;
+          uint32_t kind; TokF f;
+          const uint32_t len = toklen<W, BA, V>(x, single, p < availSC ? availSC - p : 0u, kind, f);
+          const uint32_t nr = p + len;                  // <= availSC when the token fits
+          uint32_t code = kind == TK_END ? EX_END : EX_BAD;
+          if (kind == TK_OK) code = nr < EX_FAR ? nr : (EX_FARP | p);
+          codes[j] = code;
         }
-        codes[j] = code;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(ex + skew16h(p4));
+        dst[0] = codes[0] | (codes[1] << 16); dst[1] = codes[2] | (codes[3] << 16);
       }
-      uint32_t *dst = reinterpret_cast<uint32_t *>(ex + skew16h(p4));
-      dst[0] = codes[0] | (codes[1] << 16); dst[1] = codes[2] | (codes[3] << 16);
-      __syncthreads();                               // table write front vs image read front (DecMapSmem)
-    }
-  }
-  __syncthreads();
-  // ---- phase B: chain exits.  B1: every thread sweeps one half mini-block in reverse (a code below the end of the
-  //      half points to a later entry of the same half, final already)
-  {
-    const uint32_t h0 = (uint32_t)t * DEC_HB, h1 = h0 + DEC_HB;
-    for (uint32_t p = h1; p-- > h0;)
-    {
-      uint32_t code = ex[skew16h(p)];
-      if (code < h1) { code = ex[skew16h(code)]; ex[skew16h(p)] = (uint16_t)code; }
-    }
-  }
-  __syncthreads();
-  //      B2: entries of the lower halves that exit into the upper half of their mini-block take its (final) entry
-  for (uint32_t i = t; i < DEC_SCB / 2; i += DM_T)
-  {
-    const uint32_t mb = i / DEC_HB, p = mb * DEC_MB + (i % DEC_HB);
-    const uint32_t code = ex[skew16h(p)];
-    if (code < (mb + 1) * DEC_MB) ex[skew16h(p)] = ex[skew16h(code)];
-  }
-  __syncthreads();
-  // keep the mini-block table for D3 (eight entries per 16-byte store)
-  {
-    uint4 *dst = reinterpret_cast<uint4 *>(D.exTab + (size_t)c * DEC_SCB);
-    for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
-    {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(ex + skew16h(q));
-      dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
-    }
-  }
-  __syncthreads();
-  // warp-block level, in place: inside every warp-block, mini-blocks in reverse order (a code below the end of the
-  // warp-block points into a later mini-block of the same warp-block, which is final already)
-  {
-    const uint32_t wb0 = warp * DEC_WB, wb1 = wb0 + DEC_WB;
-    for (int mb = (int)(DEC_WB / DEC_MB) - 2; mb >= 0; mb--)
-    {
-      uint32_t code[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) code[k] = ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)];
-#pragma unroll
-      for (int k = 0; k < 4; k++) if (code[k] < wb1) code[k] = ex[skew16h(code[k])];
-#pragma unroll
-      for (int k = 0; k < 4; k++) ex[skew16h(wb0 + mb * DEC_MB + lane + 32 * k)] = (uint16_t)code[k];
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  // SC level: warp-blocks in reverse order
-  for (int wb = (int)(DEC_SCB / DEC_WB) - 2; wb >= 0; wb--)
-  {
-    for (uint32_t p = wb * DEC_WB + t; p < (wb + 1) * DEC_WB; p += DM_T)
-    {
-      uint32_t code = ex[skew16h(p)];
-      if (code < DEC_SCB) { code = ex[skew16h(code)]; ex[skew16h(p)] = (uint16_t)code; }
     }
     __syncthreads();
-  }
-  // keep the SC table for D2 (as codes: D2 translates the few entries it reads)
-  {
-    uint4 *dst = reinterpret_cast<uint4 *>(D.scTab + (size_t)c * DEC_SCB);
-    for (uint32_t q = t * 8; q < DEC_SCB; q += DM_T * 8)
+    // ---- phase B: chain exits.  B1: every thread sweeps one 64-byte block in reverse (a code below the end of the block points
+    //      to a later entry of the same block, final already)
     {
-      const uint32_t *src = reinterpret_cast<const uint32_t *>(ex + skew16h(q));
-      dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
+      const uint32_t h0 = (uint32_t)t * DEC_HB, h1 = h0 + DEC_HB;
+      for (uint32_t p = h1; p-- > h0;)
+      {
+        uint32_t code = ex[skew16h(p)];
+        if (code < h1) { code = ex[skew16h(code)]; ex[skew16h(p)] = (uint16_t)code; }
+      }
+    }
+    __syncthreads();
+    //      B2: block sizes 128, 256, 512: the lower half of every block takes the (final) entry of the upper half it exits into
+#pragma unroll 1
+    for (uint32_t half = DEC_HB; half <= 256; half <<= 1)
+    {
+      for (uint32_t i = t; i < DEC_CB / 2; i += DM_T)
+      {
+        const uint32_t blk = i / half, p = blk * 2 * half + (i - blk * half);
+        const uint32_t code = ex[skew16h(p)];
+        if (code < (blk + 1) * 2 * half) ex[skew16h(p)] = ex[skew16h(code)];
+      }
+      __syncthreads();
+    }
+    //      B3: sub-chunk level, window offsets only (after B2 every entry of a 512-byte block leaves the block)
+    for (uint32_t i = t; i < DEC_NSUB * DEC_WIN; i += DM_T)
+    {
+      const uint32_t s = i / DEC_WIN, p = s * DEC_SB + (i - s * DEC_WIN);
+      const uint32_t code = ex[skew16h(p)];
+      if (code < (s + 1) * DEC_SB) ex[skew16h(p)] = ex[skew16h(code)];
+    }
+    __syncthreads();
+    // ---- the sub-chunk rows (K2 walks the sub-chunks from them)
+    {
+      uint32_t *dst = reinterpret_cast<uint32_t *>(D.subMap + (size_t)c * DEC_NSUB * DEC_WIN);
+      for (uint32_t i = t; i < DEC_NSUB * DEC_WIN / 2; i += DM_T)
+      {
+        const uint32_t s = i / (DEC_WIN / 2), p = s * DEC_SB + (i - s * (DEC_WIN / 2)) * 2;
+        dst[i] = (uint32_t)ex[skew16h(p)] | ((uint32_t)ex[skew16h(p + 1)] << 16);
+      }
+    }
+    // ---- the chunk row: chase through the sub-chunk entries (in-window hops take one look-up per sub-chunk)
+    for (uint32_t w = t; w < DEC_WIN; w += DM_T)
+    {
+      uint32_t x = ex[skew16h(w)];
+      while (x < DEC_CB) x = ex[skew16h(x)];
+      D.chunkMap[(size_t)c * DEC_WIN + w] = dec_code_abs<W, BA, V>(x, c0, S.img, single, availSC);
     }
   }
-  // absolute SC exits of the window positions
-  for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.winTab[(size_t)c * DEC_WIN + w] = dec_code_pos(ex[skew16h(w)], c0, farRow);
-}
-
-// ================================================================================================
-// D2: k_dec_chain -- one CTA per segment of DEC_SEG SCs, one thread per window offset:
-//   (1) the windowed SC-exit rows of the segment are fetched into shared memory in one round trip;
-//   (2) composed in reverse SC order: suf[i][w] = where the chain that enters SC i at window offset w leaves the
-//       SEGMENT (entries beyond the window -- after a long literal -- cost one finTab look-up per SC instead);
-//   (3) the segment's rows are published; (4) thread 0 follows the true chain from the stream start (or from the
-//       nearest chain position a preceding segment has published) through the published rows up to its own segment;
-//   (5) and walks its SCs forward through the raw rows, recording every SC's true entry.
-constexpr int DC_T = (int)DEC_WIN;
-struct DecChainSmem
-{
-  uint32_t raw[DEC_SEG][DEC_WIN];
-  uint32_t suf[DEC_SEG][DEC_WIN];
-  uint32_t ticket, entry;
-};
-constexpr int DC_LOOKBACK = 8;
-
-__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v);
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p);
-
-static __global__ void __launch_bounds__(DC_T) k_dec_chain(const DecBufs D)
-{
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  DecChainSmem &S = *reinterpret_cast<DecChainSmem *>(smemRaw);
-  DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;                 // header check of D1: uniform over the grid
-  const uint32_t w = threadIdx.x;
-  if (w == 0) S.ticket = atomicAdd(&sc.segTicket, 1u);
+  // ---- the last chunk of a segment composes the segment's rows; the last segment resolves the chain
+  const uint32_t g = c / DEC_SEG, cFirst = g * DEC_SEG, nHere = min(DEC_SEG, nChunks - cFirst);
+  __threadfence();
   __syncthreads();
-  const uint32_t g = S.ticket;
-  const uint32_t clen = sc.clen;
-  const uint32_t nSC = (clen + DEC_SCB - 1) / DEC_SCB;
-  const uint32_t nSegEff = (nSC + DEC_SEG - 1) / DEC_SEG;
-  const uint32_t cFirst = g * DEC_SEG;
-  for (uint32_t c = cFirst + w; c < min(cFirst + DEC_SEG, D.nSC); c += DC_T) D.scEntry[c] = POS_NONE;
-  if (cFirst >= nSC) return;
-  const uint32_t nHere = min(DEC_SEG, nSC - cFirst);
-  // a segment whose SCs were all jumped over by a true token (D1's scout) is never entered by the true chain: nobody will
-  // read its rows.  (The last segment still settles how the chain ended.)
-  if (__syncthreads_and(w >= nHere || D.scSkip[cFirst + w] != 0u) && g != nSegEff - 1) return;
-  const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_SCB;
-  const uint64_t segBytes = (uint64_t)DEC_SEG * DEC_SCB;
-  // (1)
-#pragma unroll 8
-  for (uint32_t i = 0; i < nHere; i++) S.raw[i][w] = __ldg(D.winTab + (size_t)(cFirst + i) * DEC_WIN + w);
-  // (1b) chains that enter a later SC of the segment beyond its window need a table look-up in global memory per
-  //      SC.  The first hops of all rows are independent of each other: take them now, many loads in flight, instead
-  //      of one dependent round trip per row inside the sequential composition below.
-  constexpr int DC_PREHOPS = 2, DC_BATCH = 16;
-#pragma unroll 1
-  for (int hop = 0; hop < DC_PREHOPS; hop++)
+  if (t == 0) S.flag = (atomicAdd(D.segCount + g, 1u) == nHere - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!S.flag) return;
+  __threadfence();
   {
-#pragma unroll 1
-    for (uint32_t i0 = 0; i0 < nHere; i0 += DC_BATCH)
+    for (uint32_t i = t; i < nHere * DEC_WIN; i += DM_T) rows[i] = __ldcg(D.chunkMap + (size_t)cFirst * DEC_WIN + i);
+    __syncthreads();
+    const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_CB;
+    for (int i = (int)nHere - 2; i >= 0; i--)
     {
-      uint32_t x[DC_BATCH], code[DC_BATCH], farv[DC_BATCH]; bool need[DC_BATCH];
-#pragma unroll
-      for (int k = 0; k < DC_BATCH; k++)
+      for (uint32_t w = t; w < DEC_WIN; w += DM_T)
       {
-        const uint32_t i = i0 + k;
-        x[k] = i < nHere ? (hop == 0 ? S.raw[i][w] : S.suf[i][w]) : POS_NONE;
-        need[k] = x[k] < POS_SPECIAL && (uint64_t)x[k] < segEnd && (x[k] % DEC_SCB) >= DEC_WIN;
-      }
-#pragma unroll
-      for (int k = 0; k < DC_BATCH; k++) code[k] = __ldg(D.scTab + (need[k] ? x[k] : 0u));          // unconditional: all in flight together
-#pragma unroll
-      for (int k = 0; k < DC_BATCH; k++)
-      {
-        const bool far = need[k] && code[k] >= EX_FARP;
-        // (the dummy address of the not-far case is a word that is always initialised: the scalars D1 wrote)
-        farv[k] = __ldcg(far ? D.farTab + ((size_t)(x[k] / DEC_SCB) * DEC_SCB + (code[k] & 0x3FFFu)) : reinterpret_cast<const uint32_t *>(D.sc));
-      }
-#pragma unroll
-      for (int k = 0; k < DC_BATCH; k++)
-      {
-        const uint32_t i = i0 + k;
-        if (i >= nHere) continue;
-        uint32_t y = x[k];
-        if (need[k])
+        const uint32_t x = rows[i * DEC_WIN + w];
+        if (x < POS_SPECIAL && (uint64_t)x < segEnd)
         {
-          const uint32_t c0 = (x[k] / DEC_SCB) * DEC_SCB;
-          y = code[k] < EX_FAR ? c0 + code[k] : code[k] < EX_FARP ? (code[k] == EX_END ? POS_END : POS_BAD) : farv[k];
+          const uint32_t c2 = x / DEC_CB, off = x - c2 * DEC_CB;
+          if (off < DEC_WIN) rows[i * DEC_WIN + w] = rows[(c2 - cFirst) * DEC_WIN + off];      // a later chunk of the segment: final already
         }
-        S.suf[i][w] = y;
       }
+      __syncthreads();
     }
-  }
-  __syncthreads();
-  // (2)
-  for (int i = (int)nHere - 1; i >= 0; i--)
-  {
-    uint32_t x = S.suf[i][w];
-    while (x < POS_SPECIAL && (uint64_t)x < segEnd)
-    {
-      const uint32_t c2 = x / DEC_SCB, off = x - c2 * DEC_SCB;
-      if (off < DEC_WIN) { x = S.suf[c2 - cFirst][off]; break; }    // a later SC of the segment: final already
-      x = dec_sc_exit(D, x);                                        // entry beyond the window: one SC at a time
-    }
-    S.suf[i][w] = x;
-    __syncthreads();
-  }
-  // (3)
-  {
-    uint32_t *dst = D.sufExit + (size_t)cFirst * DEC_WIN;
-    for (uint32_t i = 0; i < nHere; i++) dst[i * DEC_WIN + w] = S.suf[i][w];
+    for (uint32_t i = t; i < nHere * DEC_WIN; i += DM_T) D.sufMap[(size_t)cFirst * DEC_WIN + i] = rows[i];
   }
   __threadfence();
   __syncthreads();
-  if (w == 0)
-  {
-    st_volatile_u32(D.flagSeg + g, 1u);
-    // (4)
-    uint32_t pos = sc.first;
-    for (int k = (int)g - 1; k >= 0 && k >= (int)g - DC_LOOKBACK; k--)
-      if (ld_volatile_u32(D.chainFlag + k)) { __threadfence(); pos = __ldcg(D.chainPos + k); break; }
-    while (pos < POS_SPECIAL && pos < clen && (uint64_t)pos / segBytes < g)
-    {
-      const uint32_t c = pos / DEC_SCB, off = pos - c * DEC_SCB;
-      if (off < DEC_WIN)
-      { // rows are zeroed per call and an exit is never 0: the entry itself tells whether its segment has published
-        uint32_t v;
-        do { v = ld_volatile_u32(D.sufExit + (size_t)c * DEC_WIN + off); } while (v == 0u);
-        pos = v;
-      }
-      else pos = dec_sc_exit(D, pos);
-    }
-    // pos: the first position of the true chain at or after the start of this segment (or how the chain ended)
-    D.chainPos[g] = pos; __threadfence(); st_volatile_u32(D.chainFlag + g, 1u);
-    S.entry = (pos < POS_SPECIAL && pos < clen && (uint64_t)pos < segEnd) ? pos : POS_NONE;
-    if (g == nSegEff - 1)
-    { // the last segment settles whether the chain reaches the terminator
-      uint32_t x = pos;
-      while (x < POS_SPECIAL)
-      {
-        if (x >= clen) { x = POS_BAD; break; }
-        const uint32_t c = x / DEC_SCB, off = x - c * DEC_SCB;
-        x = off < DEC_WIN ? S.suf[c - cFirst][off] : dec_sc_exit(D, x);
-      }
-      if (x != POS_END) sc.status = ST_BADSTREAM;
-    }
-    // (5)
-    uint32_t p = S.entry;
-    while (p < POS_SPECIAL && (uint64_t)p < segEnd && p < clen)
-    {
-      const uint32_t c = p / DEC_SCB, off = p - c * DEC_SCB;
-      D.scEntry[c] = p;
-      p = off < DEC_WIN ? S.raw[c - cFirst][off] : dec_sc_exit(D, p);
-    }
-  }
+  if (t == 0) S.flag = (atomicAdd(&D.cnt->segsDone, 1u) == nSeg - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!S.flag) return;
+  __threadfence();
+  dec_resolve<W, BA, V>(D, hs, S, rows);
 }
 
 // ================================================================================================
-// D3: k_dec_emit -- token walk, scan over the SCs (decoupled look-back), expansion; k_dec_big -- grid-wide long ops
-constexpr int DX_T = 256;                   // threads per SC (the first DEC_T of them walk one mini-block each)
-constexpr int DX_GROUP = DX_T;              // look-back group: aggregates of the group + inclusive prefix of the group before
-constexpr uint32_t DX_LONG_VECS = 256;      // literal copies / run fills of more 16-byte vectors than this are done by the whole CTA
-constexpr uint32_t DX_HUGE_VECS = 16384;    // ... and from here on (256 KiB) by the whole grid (k_dec_big)
-constexpr int DX_BIGCAP = 96;
+// K2: k_dec_emit -- persistent CTAs: chunk entry, token walk, look-back over the chunks, expansion, grid-wide long operations
+constexpr int DX_T = 256;
+constexpr uint32_t DX_INLINE = 64;          // token parts up to this many bytes (inside a tile) are written by the token's own thread
+constexpr int DX_NSKIP = 16;                // whole-tile ranges of a chunk handed to the grid
+constexpr uint32_t DX_LONGCAP = DEC_TILE / DX_INLINE * 2 + 8;
 
 template <int K> struct DecEmitSmem
 {
-  alignas(16) uint8_t data[DEC_DATA_BYTES];    // skewed SC image
-  union
-  {
-    alignas(16) uint16_t ex[DEC_SCB];          // exit table from D1 (linear), only needed to mark the chain
-    struct
-    {
-      uint64_t tSym[DEC_TOKCAP];               // token records of an expansion pass
-      uint32_t tOut[DEC_TOKCAP + 4];
-      uint32_t tLitLen[DEC_TOKCAP];
-      uint32_t tLitSrc[DEC_TOKCAP];
-    } rec;
-  } u;
-  uint32_t mbEntry[DEC_T];                     // SC-relative entry of the true chain into every mini-block (or 0xFFFF)
-  DecAgg<K> warpAgg[DX_T / 32 + 1];
-  DecAgg<K> bc;
-  DecBigOp big[DX_BIGCAP];
-  uint4 lowMask[17];                           // lowMask[i]: the bytes below i of a 16-byte vector
-  uint32_t nBig, ticket, flag;
+  alignas(16) uint8_t img[DEC_IMG_BYTES];           // chunk image + pad (bulk-copy destination)
+  alignas(16) uint8_t tile[DEC_TILE];                // output image of one expansion step (also: staging of chunk rows / bulk literal source)
+  uint64_t rSym[DEC_NSLOT];                           // token records of an expansion pass: run symbol (first period) ...
+  uint32_t rOut[DEC_NSLOT + 4];                       // ... output offset relative to the chunk's first output byte (+ sentinel) ...
+  uint32_t rLit[DEC_NSLOT];                           // ... literal bytes ...
+  uint32_t rRun[DEC_NSLOT];                           // ... run bytes ...
+  uint32_t rSrc[DEC_NSLOT];                           // ... literal source relative to the chunk start
+  alignas(16) uint16_t sub[DEC_NSUB][DEC_WIN];        // sub-chunk rows of the chunk
+  uint32_t subEntry[DEC_NSUB];
+  uint32_t subCnt[DEC_NSUB + 1];                      // tokens per sub-chunk -> exclusive prefix
+  uint64_t subOut[DEC_NSUB + 1];                      // output bytes per sub-chunk -> exclusive prefix (relative to the chunk)
+  uint64_t subSym[DEC_NSUB];                          // K == 0: symbol register at the start of the sub-chunk
+  Lut subLut[K ? DEC_NSUB : 1];                       // K > 0: table at the start of the sub-chunk
+  DecAgg<K> bc;                                       // look-back result
+  uint32_t longList[DX_LONGCAP];
+  uint32_t skipLo[DX_NSKIP], skipHi[DX_NSKIP];
+  alignas(8) unsigned long long mbar[2];
+  uint32_t nLong, nSkip, ticket, entry, flag, bcast;
 };
-
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
-{
-  uint32_t v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
-{
-  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+static_assert(DEC_TILE + DEC_NSLOT * 24 >= (DEC_SEG - 1) * DEC_WIN * 4, "chunk rows fit the tile + record area");
 
 // field-wise helpers (K == 0 aggregates carry no LUT transform: nothing of it is moved)
+template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_down(const DecAgg<K> &v, int d)
+{
+  DecAgg<K> r;
+  r.out = __shfl_down_sync(0xFFFFFFFFu, v.out, d);
+  r.ntok = __shfl_down_sync(0xFFFFFFFFu, v.ntok, d);
+  r.symPos = __shfl_down_sync(0xFFFFFFFFu, v.symPos, d);
+  if (K)
+  {
+#pragma unroll
+    for (int i = 0; i < 7; i++) if (i < K) r.xf.e[i] = __shfl_down_sync(0xFFFFFFFFu, v.xf.e[i], d);
+  }
+  return r;
+}
 template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_up(const DecAgg<K> &v, int d)
 {
   DecAgg<K> r;
   r.out = __shfl_up_sync(0xFFFFFFFFu, v.out, d);
   r.ntok = __shfl_up_sync(0xFFFFFFFFu, v.ntok, d);
-  r.has = __shfl_up_sync(0xFFFFFFFFu, v.has, d);
-  r.sym = __shfl_up_sync(0xFFFFFFFFu, v.sym, d);
+  r.symPos = __shfl_up_sync(0xFFFFFFFFu, v.symPos, d);
   if (K)
   {
 #pragma unroll
@@ -570,7 +496,7 @@ template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_up(const DecAg
 }
 template <int K> __device__ __forceinline__ void decagg_store(DecAgg<K> *dst, const DecAgg<K> &v)
 {
-  dst->out = v.out; dst->ntok = v.ntok; dst->has = v.has; dst->sym = v.sym;
+  dst->out = v.out; dst->ntok = v.ntok; dst->symPos = v.symPos;
   if (K)
   {
 #pragma unroll
@@ -581,7 +507,7 @@ template <int K> __device__ __forceinline__ void decagg_store(DecAgg<K> *dst, co
 template <int K> __device__ __forceinline__ DecAgg<K> decagg_load_cg(const DecAgg<K> *src)
 {
   DecAgg<K> r = decagg_identity<K>();
-  r.out = __ldcg(&src->out); r.ntok = __ldcg(&src->ntok); r.has = __ldcg(&src->has); r.sym = __ldcg(&src->sym);
+  r.out = __ldcg(&src->out); r.ntok = __ldcg(&src->ntok); r.symPos = __ldcg(&src->symPos);
   if (K)
   {
 #pragma unroll
@@ -590,89 +516,17 @@ template <int K> __device__ __forceinline__ DecAgg<K> decagg_load_cg(const DecAg
   return r;
 }
 
-// exclusive scan over the CTA in thread order; total = combination of everything.  warpBuf holds nWarps + 1 entries.
-template <int K> __device__ __forceinline__ DecAgg<K> dec_block_excl_scan(DecAgg<K> *warpBuf, const DecAgg<K> &mine, DecAgg<K> &total)
+// ---- output helpers
+// 16 bytes of the period-W pattern `sym` starting at pattern offset ph (0 <= ph < W)
+template <int W> __device__ __forceinline__ uint4 dec_run_vec(uint64_t sym, uint32_t ph)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = blockDim.x >> 5;
-  DecAgg<K> inc = mine;
+  uint32_t w[4];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1)
-  {
-    const DecAgg<K> o = decagg_shfl_up<K>(inc, d);
-    if (lane >= d) inc = decagg_combine<K>(o, inc);
-  }
-  if (lane == 31) decagg_store<K>(&warpBuf[warp], inc);
-  DecAgg<K> ex = decagg_shfl_up<K>(inc, 1);
-  if (lane == 0) ex = decagg_identity<K>();
-  __syncthreads();
-  if (warp == 0)
-  { // the warp totals are scanned by one warp: exclusive prefix per warp, grand total in slot nw
-    DecAgg<K> w = decagg_identity<K>();
-    if (lane < nw) w = warpBuf[lane];
-    for (int d = 1; d < nw; d <<= 1)
-    {
-      const DecAgg<K> o = decagg_shfl_up<K>(w, d);
-      if (lane >= d) w = decagg_combine<K>(o, w);
-    }
-    DecAgg<K> wex = decagg_shfl_up<K>(w, 1);
-    if (lane == 0) wex = decagg_identity<K>();
-    if (lane < nw) decagg_store<K>(&warpBuf[lane], wex);
-    if (lane == nw - 1) decagg_store<K>(&warpBuf[nw], w);
-  }
-  __syncthreads();
-  const DecAgg<K> pre = warpBuf[warp];
-  total = warpBuf[nw];
-  __syncthreads();
-  return decagg_combine<K>(pre, ex);
+  for (int j = 0; j < 4; j++) w[j] = pattern_word(sym, W, (ph + 4 * j) % W);
+  return make_uint4(w[0], w[1], w[2], w[3]);
 }
-
-// sizes and symbol summary of the tokens of my mini-block (walk #1)
-template <int W, int BA, int V>
-__device__ __forceinline__ void dec_walk_sizes(const uint8_t *data, uint32_t myEntry, uint32_t c0, uint32_t clen, bool single,
-                                               DecAgg<make_spec(W, BA, V).K> &mine, bool &sawEnd, bool &sawBad)
-{
-  constexpr Spec sp = make_spec(W, BA, V);
-  constexpr int K = sp.K;
-  uint32_t p = myEntry;
-  const uint32_t b1 = (p / DEC_MB + 1) * DEC_MB;
-  while (p < b1)
-  {
-    SkewReader rd; rd.data = data; rd.p = p;
-    Tok tk; dec_parse_rd(sp, single, rd, (uint64_t)clen - (c0 + p), tk);
-    if (c0 + p >= clen || !tk.valid) { sawBad = true; break; }
-    mine.out += (uint64_t)tk.litLen + tk.runLen; mine.ntok++;
-    if (K)
-    {
-      const int idx = tk.symKind == 0 ? K : tk.symKind - 2;
-      lutxf_touch(mine.xf, K, idx, c0 + p + tk.symOff);
-    }
-    else if (tk.symKind == 0) { mine.has = 1; mine.sym = rd_sym(rd, tk.symOff, W); }
-    if (tk.last) { sawEnd = true; break; }
-    const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
-    p = nx < DEC_SCB ? (uint32_t)nx : DEC_SCB;
-  }
-}
-
-// symbol of a token given the running symbol state; updates the state
-template <int W, int BA, int V>
-__device__ __forceinline__ uint64_t dec_token_symbol(const Tok &t, const SkewReader &rd, uint64_t &symReg, Lut &lut)
-{
-  constexpr Spec sp = make_spec(W, BA, V);
-  constexpr int K = sp.K;
-  if (K)
-  {
-    const int idx = t.symKind == 0 ? K : t.symKind - 2;
-    if (idx == K) lut_touch(lut, K, K, rd_sym(rd, t.symOff, W));
-    else if (idx > 0) { const uint64_t v = lut_get(lut, K, idx); lut_touch(lut, K, idx, v); }
-    return lut.s[0];
-  }
-  if (t.symKind == 0) symReg = rd_sym(rd, t.symOff, W);
-  return symReg;
-}
-
-// ---- 16-byte output vectors
-// stream bytes [src, src+16) (any alignment; only aligned words holding at least one of them are read)
+template <int W> __device__ __forceinline__ uint32_t run_byte(uint64_t sym, uint32_t ph) { return (uint32_t)(sym >> (8 * ph)) & 0xFFu; }
+// global stream bytes [src, src+16) (any alignment; only aligned words holding at least one of them are read)
 __device__ __forceinline__ uint4 dec_lit_vec(const uint8_t *__restrict__ in, uint32_t src)
 {
   const uint32_t sb = src & 3u;
@@ -682,62 +536,63 @@ __device__ __forceinline__ uint4 dec_lit_vec(const uint8_t *__restrict__ in, uin
   const uint32_t w4 = __ldg(sw + 4), sh = sb * 8;
   return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
-// as dec_lit_vec for a vector of which only bytes [a, b) (0 <= a < b <= 16) are needed: words holding none of them are
-// not read (they may lie before the stream or after its end), `src` may be negative
-__device__ __forceinline__ uint4 dec_lit_vec_part(const uint8_t *__restrict__ in, int64_t src, uint32_t a, uint32_t b)
+// shared-memory bytes [p, p+16) of a byte array (any alignment)
+__device__ __forceinline__ uint4 smem_vec(const uint8_t *base, uint32_t p)
 {
-  const uint32_t sb = (uint32_t)src & 3u;
-  const uint8_t *base = in + (src - (int64_t)sb);                  // aligned stream position of word 0
-  uint32_t w[5];
-#pragma unroll
-  for (int k = 0; k < 5; k++)
-  { // word k holds the vector bytes [4k - sb, 4k - sb + 4)
-    const int v0 = 4 * k - (int)sb;
-    w[k] = (v0 < (int)b && v0 + 4 > (int)a) ? __ldg(reinterpret_cast<const uint32_t *>(base + 4 * k)) : 0u;
-  }
-  const uint32_t sh = sb * 8;
-  return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
-}
-// 16 bytes of the period-W pattern `sym` starting at pattern offset ph (0 <= ph < W)
-template <int W> __device__ __forceinline__ uint4 dec_run_vec(uint64_t sym, uint32_t ph)
-{
-  uint32_t w[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) w[j] = pattern_word(sym, W, (ph + 4 * j) % W);
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-template <int W> __device__ __forceinline__ void dec_big_vec(const DecBigOp &op, uint32_t k, const uint8_t *__restrict__ in, uint8_t *__restrict__ out)
-{ // vector k of a long operation
-  const uint32_t v = op.v0 + k;
-  uint4 x;
-  if (op.kind == 0) x = dec_lit_vec(in, op.src + 16u * k);
-  else x = dec_run_vec<W>(op.sym, (uint32_t)(((uint64_t)v * 16 - op.src) % (uint32_t)W));
-  *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = x;
+  const uint32_t *sw = reinterpret_cast<const uint32_t *>(base) + (p >> 2);
+  const uint32_t sh = (p & 3u) * 8u;
+  const uint32_t w0 = sw[0], w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4];
+  return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
 }
 
-// the CTA's last act: the last CTA of the grid settles the status and the result
-__device__ __forceinline__ void dec_emit_done(const DecBufs &D, uint32_t *flagSlot)
+// one literal byte of a token of the current chunk: from the image when it holds it, else from the stream
+__device__ __forceinline__ uint32_t lit_byte(const uint8_t *img, const uint8_t *__restrict__ in, uint32_t c0, uint32_t rel)
 {
-  __syncthreads();
-  if (threadIdx.x == 0)
+  return rel < DEC_CB + DEC_IMG_PAD ? (uint32_t)img[rel] : (uint32_t)__ldg(in + (size_t)c0 + rel);
+}
+
+// run fill of `len` bytes at tile offset d by one warp: byte head to the next 16-byte boundary, vectors, byte tail
+template <int W> __device__ __forceinline__ void warp_fill(uint8_t *tile, uint32_t d, uint32_t len, uint64_t sym, uint32_t ph, int lane)
+{
+  const uint32_t head = min(len, (16u - (d & 15u)) & 15u);
+  if ((uint32_t)lane < head) tile[d + lane] = (uint8_t)run_byte<W>(sym, (ph + lane) % W);
+  const uint32_t d1 = d + head, nv = (len - head) >> 4, ph1 = (ph + head) % W;
+  for (uint32_t v = lane; v < nv; v += 32) *reinterpret_cast<uint4 *>(tile + d1 + 16 * v) = dec_run_vec<W>(sym, (ph1 + 16 * v) % W);
+  const uint32_t done = head + (nv << 4), tail = len - done;
+  if ((uint32_t)lane < tail) tile[d + done + lane] = (uint8_t)run_byte<W>(sym, (ph + done + lane) % W);
+}
+// literal copy of `len` bytes to tile offset d by one warp; source = chunk-relative stream position rel
+__device__ __forceinline__ void warp_copy(uint8_t *tile, uint32_t d, uint32_t len, const uint8_t *img, const uint8_t *__restrict__ in, uint32_t c0, uint32_t rel, int lane)
+{
+  const uint32_t head = min(len, (16u - (d & 15u)) & 15u);
+  if ((uint32_t)lane < head) tile[d + lane] = (uint8_t)lit_byte(img, in, c0, rel + lane);
+  const uint32_t d1 = d + head, nv = (len - head) >> 4, r1 = rel + head;
+  for (uint32_t v = lane; v < nv; v += 32)
   {
-    __threadfence();
-    *flagSlot = (atomicAdd(&D.sc->done, 1u) == gridDim.x - 1) ? 1u : 0u;
-    if (*flagSlot)
-    {
-      __threadfence();
-      DecScalars &sc = *D.sc;
-      uint32_t status = ld_volatile_u32(&sc.status);
-      if (status == ST_OK)
-      {
-        const uint32_t bad = ld_volatile_u32(&sc.emitBad), end = ld_volatile_u32(&sc.endSeen);
-        const unsigned long long tot = ld_volatile_u64(&sc.outTotal);
-        if (bad || !end || tot != (unsigned long long)sc.n) { status = ST_BADSTREAM; sc.status = status; }
-      }
-      D.dResult[0] = status == ST_OK ? sc.n : 0; D.dResult[1] = status; D.dResult[2] = ld_volatile_u32(&sc.nTok); D.dResult[3] = D.nSC;
-      D.dResult[4] = sc.clen; D.dResult[5] = sc.single; D.dResult[6] = ld_volatile_u32(&sc.nHuge); D.dResult[7] = 0;
-    }
+    const uint32_t r = r1 + 16 * v;
+    const uint4 x = (r + 20 <= DEC_CB + DEC_IMG_PAD) ? smem_vec(img, r) : dec_lit_vec(in, c0 + r);
+    *reinterpret_cast<uint4 *>(tile + d1 + 16 * v) = x;
   }
+  const uint32_t done = head + (nv << 4), tail = len - done;
+  if ((uint32_t)lane < tail) tile[d + done + lane] = (uint8_t)lit_byte(img, in, c0, rel + done + lane);
+}
+
+// one piece (<= DEC_BIG_PIECE bytes, 16-byte aligned destination) of a grid-wide operation, by the whole CTA
+template <int W, int K>
+__device__ void dec_big_piece(const DecBufs &D, DecEmitSmem<K> &S, const DecBigOp &op, uint32_t off, uint32_t len, uint32_t &phase0, uint32_t &phase1)
+{
+  const int t = threadIdx.x;
+  uint8_t *__restrict__ out = D.out + (size_t)op.dst + off;
+  if (op.kind == 1)
+  { // run fill: pattern phase of the piece's first byte
+    const uint32_t ph0 = (uint32_t)(((uint64_t)op.dst + off - op.src) % (uint32_t)W);
+    for (uint32_t v = t; v < (len >> 4); v += DX_T) reinterpret_cast<uint4 *>(out)[v] = dec_run_vec<W>(op.sym, (ph0 + 16 * v) % W);
+    return;
+  }
+  // literal copy: unaligned source words straight from the stream (L2), 16-byte stores
+  const uint32_t src0 = op.src + off;                       // stream position of the piece's first byte
+  (void)S; (void)phase0; (void)phase1;
+  for (uint32_t v = t; v < (len >> 4); v += DX_T) reinterpret_cast<uint4 *>(out)[v] = dec_lit_vec(D.in, src0 + 16u * v);
 }
 
 template <int W, int BA, int V>
@@ -749,292 +604,457 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   using Smem = DecEmitSmem<K>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
-  DecScalars &sc = *D.sc;
-  const int t = threadIdx.x;
-  // status as the kernels before left it: uniform over the grid (errors found here go to sc.emitBad)
-  if (sc.status != ST_OK) { dec_emit_done(D, &S.flag); return; }
-  if (t == 0) { S.ticket = atomicAdd(&sc.ticket, 1u); S.nBig = 0; }
-  if (t < 17)
-  {
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { const int nb = min(max(t - 4 * k, 0), 4); w[k] = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u); }
-    S.lowMask[t] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  __syncthreads();
-  const uint32_t c = S.ticket, c0 = c * DEC_SCB;
-  const uint32_t clen = sc.clen, n = sc.n;
-  const bool single = sc.single != 0;
-  Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
-  const uint32_t entry = D.scEntry[c];
-  const bool hasTok = entry < POS_SPECIAL;
-  if (!hasTok && c != gridDim.x - 1 && (c % DX_GROUP) != DX_GROUP - 1)
-  { // no token starts in this SC (it lies inside a long literal) and nobody needs its prefix: publish the identity and go
-    if (t == 0) { decagg_store<K>(&aggBuf[c], decagg_identity<K>()); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
-    dec_emit_done(D, &S.flag);
+  const DecScalars hs = *D.sc;
+  DecCounters &cnt = *D.cnt;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (hs.status != ST_OK)
+  { // header check of K1 failed: uniform over the grid
+    if (blockIdx.x == 0 && t == 0) { D.dResult[0] = 0; D.dResult[1] = hs.status; for (int i = 2; i < 8; i++) D.dResult[i] = 0; }
     return;
   }
-
-  // ---- the SC's tokens: chain marks, walk #1
-  Agg mine = decagg_identity<K>();
-  uint32_t myEntry = 0xFFFFu;
-  if (hasTok)
-  {
-    dec_load_sc(S.data, D.in, c0, clen);
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(D.exTab + (size_t)c * DEC_SCB);
-      uint4 *dst = reinterpret_cast<uint4 *>(S.u.ex);
-      for (uint32_t v = t; v < DEC_SCB * 2 / 16; v += DX_T) dst[v] = __ldg(src + v);
-    }
-    if (t < DEC_T) S.mbEntry[t] = 0xFFFFu;
-    __syncthreads();
-    if (t == 0)
-    {
-      uint32_t p = entry - c0;
-      while (p < DEC_SCB)
-      {
-        S.mbEntry[p / DEC_MB] = p;
-        const uint32_t code = S.u.ex[p];
-        p = code < EX_FAR ? code : DEC_SCB;          // leaves the SC (or ends / breaks inside this mini-block)
-      }
-    }
-    __syncthreads();
-    bool sawEnd = false, sawBad = false;
-    if (t < DEC_T)
-    {
-      myEntry = S.mbEntry[t];
-      if (myEntry != 0xFFFFu) dec_walk_sizes<W, BA, V>(S.data, myEntry, c0, clen, single, mine, sawEnd, sawBad);
-    }
-    if (sawBad) sc.emitBad = 1;
-    if (sawEnd) sc.endSeen = 1;
-  }
-  Agg total;
-  const Agg pre = dec_block_excl_scan<K>(S.warpAgg, mine, total);
-
-  // ---- scan over the SCs: publish my aggregate, gather the group's aggregates and the prefix of the group before
-  if (t == 0) { decagg_store<K>(&aggBuf[c], total); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
-  const uint32_t g0 = (c / DX_GROUP) * DX_GROUP;
-  Agg part = decagg_identity<K>();
-  {
-    const uint32_t p = g0 + t;
-    if (p < c)
-    {
-      while (ld_volatile_u32(D.flagAgg + p) == 0u) { }
-      __threadfence();
-      part = decagg_load_cg<K>(&aggBuf[p]);
-    }
-  }
-  Agg exclusive;
-  (void)dec_block_excl_scan<K>(S.warpAgg, part, exclusive);
-  if (g0 > 0)
-  {
-    if (t == 0)
-    {
-      while (ld_volatile_u32(D.flagInc + (g0 - 1)) == 0u) { }
-      __threadfence();
-      const Agg before = decagg_load_cg<K>(&incBuf[g0 - 1]);
-      decagg_store<K>(&S.bc, before);
-    }
-    __syncthreads();
-    const Agg before = S.bc;
-    exclusive = decagg_combine<K>(before, exclusive);
-  }
-  const bool lastOfGrid = c == gridDim.x - 1;
-  if (t == 0 && ((c % DX_GROUP) == DX_GROUP - 1 || lastOfGrid))
-  {
-    const Agg inclusive = decagg_combine<K>(exclusive, total);
-    decagg_store<K>(&incBuf[c], inclusive); __threadfence(); st_volatile_u32(D.flagInc + c, 1u);
-    if (lastOfGrid) { st_volatile_u64(&sc.outTotal, inclusive.out); st_volatile_u32(&sc.nTok, inclusive.ntok); }
-  }
-  if (!hasTok || total.ntok == 0) { dec_emit_done(D, &S.flag); return; }
-
-  // ---- state at the start of my mini-block
-  const Agg before = decagg_combine<K>(exclusive, pre);
-  uint64_t symReg = single ? (uint64_t)sc.singleSym : before.sym;     // register starts as zero (src/rleX_extreme_cpu_decode.h:33)
-  Lut lut; lut_init(lut, W);
-  if (K && myEntry != 0xFFFFu) { Lut l0 = lut; lutxf_apply(before.xf, K, W, D.in, l0, lut); }
-  uint64_t outPos = before.out;
-  const uint64_t scOut1 = exclusive.out + total.out;
-  uint64_t *tSym = S.u.rec.tSym;
-  uint32_t *tOut = S.u.rec.tOut, *tLitLen = S.u.rec.tLitLen, *tLitSrc = S.u.rec.tLitSrc;
+  const uint32_t clen = hs.clen, n = hs.n;
+  const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB;
+  const bool single = hs.single != 0;
   const uint8_t *__restrict__ in = D.in;
   uint8_t *__restrict__ out = D.out;
+  Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
+  uint32_t *const rowStage = reinterpret_cast<uint32_t *>(S.tile);   // chunk rows for the entry derivation (tile + record area)
+  if (t == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); }
+  uint32_t phase0 = 0, phase1 = 0;
+  __syncthreads();
+#define HSRLE_DBG(code) do { if (D.dbg && t == 0) { *((volatile uint32_t *)D.dbg + blockIdx.x) = (uint32_t)(code); __threadfence_system(); } } while (0)
 
-  // ---- expansion in passes of DEC_TOKCAP tokens
-  uint32_t p = myEntry == 0xFFFFu ? DEC_SCB : myEntry;
-  uint32_t k = pre.ntok;                                               // my next token index inside the SC
-  const uint32_t b1 = (t + 1) * DEC_MB;
-  for (uint32_t pass0 = 0; pass0 < total.ntok; pass0 += DEC_TOKCAP)
+  for (;;)
   {
-    const uint32_t passN = min(DEC_TOKCAP, total.ntok - pass0);
-    __syncthreads();                                                   // the exit table / the previous pass's records are dead
-    if (t < DEC_T)
-    {
-      while (p < b1 && k < pass0 + passN)
-      {
-        SkewReader rd; rd.data = S.data; rd.p = p;
-        Tok tk; dec_parse_rd(sp, single, rd, (uint64_t)clen - (c0 + p), tk);
-        if (!tk.valid) { p = DEC_SCB; break; }
-        const uint64_t sym = dec_token_symbol<W, BA, V>(tk, rd, symReg, lut);
-        const uint32_t r = k - pass0;
-        tOut[r] = (uint32_t)min(outPos, (uint64_t)n); tLitLen[r] = tk.litLen; tLitSrc[r] = c0 + p + tk.hdrLen; tSym[r] = sym;
-        outPos += (uint64_t)tk.litLen + tk.runLen; k++;
-        if (tk.last) { p = DEC_SCB; break; }
-        const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
-        p = nx < DEC_SCB ? (uint32_t)nx : DEC_SCB;
-      }
-      // sentinel: start of the first token of the next pass (written by its owner), or the end of the SC's output
-      if (k == pass0 + passN && p < b1 && pass0 + passN < total.ntok) tOut[passN] = (uint32_t)min(outPos, (uint64_t)n);
-      if (pass0 + passN >= total.ntok && t == 0) tOut[passN] = (uint32_t)min(scOut1, (uint64_t)n);   // never write beyond the declared size
-    }
     __syncthreads();
-    const uint32_t pStart = tOut[0], pEnd = tOut[passN];
-    if (pStart >= pEnd) continue;
-
-    // -- phase M: vectors that mix segments (literal / run of neighbouring tokens), one owning token per thread;
-    //    item passN is the partial vector at the start of the pass (its first bytes belong to the pass / SC before).
-    //    A vector is assembled segment by segment: 16 bytes of literal source or run pattern, masked to the segment.
-    {
-      auto mixed = [&](uint32_t vb, uint32_t r0)
-      { // all positions are output offsets <= pEnd <= n: 32-bit arithmetic throughout
-        const uint32_t lo = max(vb, pStart), hi = (vb > 0xFFFFFFEFu || pEnd - vb < 16u) ? pEnd : vb + 16u;
-        uint32_t rr = r0;
-        uint32_t tStart = tOut[rr], tNext = tOut[rr + 1];
-        uint32_t litLen = tLitLen[rr];
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        uint32_t x = lo;
-        while (x < hi)
-        {
-          while (x >= tNext) { rr++; tStart = tNext; tNext = tOut[rr + 1]; litLen = tLitLen[rr]; }
-          const uint32_t litEnd = litLen >= tNext - tStart ? tNext : tStart + litLen;
-          uint4 cv; uint32_t segEnd;
-          if (x < litEnd)
-          {
-            segEnd = min(litEnd, hi);
-            cv = dec_lit_vec_part(in, (int64_t)tLitSrc[rr] + ((int64_t)vb - (int64_t)tStart), x - vb, segEnd - vb);
-          }
-          else
-          {
-            segEnd = min(tNext, hi);
-            cv = dec_run_vec<W>(tSym[rr], (vb + 48u - litEnd) % (uint32_t)W);     // small and positive even if vb + 48 wraps
-          }
-          const uint4 mb = S.lowMask[segEnd - vb], ma = S.lowMask[x - vb];   // bytes [x, segEnd) of the vector
-          a0 |= cv.x & mb.x & ~ma.x; a1 |= cv.y & mb.y & ~ma.y;
-          a2 |= cv.z & mb.z & ~ma.z; a3 |= cv.w & mb.w & ~ma.w;
-          x = segEnd;
-        }
-        if (lo == vb && hi - vb == 16u) *reinterpret_cast<uint4 *>(out + vb) = make_uint4(a0, a1, a2, a3);
-        else
-        {
-          const uint32_t ba = lo - vb, bb = hi - vb;
-#pragma unroll
-          for (int i = 0; i < 16; i++)
-          {
-            const uint32_t wv = (i >> 2) == 0 ? a0 : (i >> 2) == 1 ? a1 : (i >> 2) == 2 ? a2 : a3;
-            if ((uint32_t)i >= ba && (uint32_t)i < bb) out[(size_t)vb + i] = (uint8_t)(wv >> (8 * (i & 3)));
-          }
-        }
-      };
-      for (uint32_t r = t; r <= passN; r += DX_T)
-      {
-        if (r == passN) { if (pStart & 15u) mixed(pStart & ~15u, 0); }
-        else
-        {
-          const uint32_t o = tOut[r], o1 = tOut[r + 1];
-          const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
-          if (m > o && (m & 15u) && (m & ~15u) >= o) mixed(m & ~15u, r);
-          if (o1 > m && (o1 & 15u) && (o1 & ~15u) >= m) mixed(o1 & ~15u, r);
-        }
-      }
-    }
-
-    // -- phase F: vectors inside one literal / one run, eight lanes per token; long ones are deferred
-    {
-      auto defer = [&](const DecBigOp &op)
-      {
-        if (op.nv >= DX_HUGE_VECS) { D.hugeList[atomicAdd(&sc.nHuge, 1u)] = op; return; }
-        const uint32_t slot = atomicAdd(&S.nBig, 1u);
-        if (slot < (uint32_t)DX_BIGCAP) S.big[slot] = op;
-        else D.medList[atomicAdd(&sc.nMed, 1u)] = op;        // more long operations than the CTA's list holds: k_dec_big
-      };
-      const int grp = t >> 3, l8 = t & 7;
-      for (uint32_t r = grp; r < passN; r += DX_T / 8)
-      {
-        const uint32_t o = tOut[r], o1 = tOut[r + 1];
-        const uint32_t m = (uint32_t)min((uint64_t)o + tLitLen[r], (uint64_t)o1);
-        { // literal: vectors [ceil(o/16), floor(m/16))
-          const uint32_t v0 = (o >> 4) + ((o & 15u) ? 1u : 0u), v1 = m >> 4;
-          if (v1 > v0)
-          {
-            const uint32_t src0 = tLitSrc[r] + (v0 * 16u - o);
-            if (v1 - v0 > DX_LONG_VECS)
-            {
-              if (l8 == 0)
-              {
-                DecBigOp op; op.v0 = v0; op.nv = v1 - v0; op.src = src0; op.kind = 0; op.sym = 0;
-                defer(op);
-              }
-            }
-            else for (uint32_t v = v0 + l8; v < v1; v += 8) *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = dec_lit_vec(in, src0 + (v - v0) * 16u);
-          }
-        }
-        { // run: vectors [ceil(m/16), floor(o1/16))
-          const uint32_t v0 = (m >> 4) + ((m & 15u) ? 1u : 0u), v1 = o1 >> 4;
-          if (v1 > v0)
-          {
-            const uint64_t sym = tSym[r];
-            if (v1 - v0 > DX_LONG_VECS)
-            {
-              if (l8 == 0)
-              {
-                DecBigOp op; op.v0 = v0; op.nv = v1 - v0; op.src = m; op.kind = 1; op.sym = sym;
-                defer(op);
-              }
-            }
-            else for (uint32_t v = v0 + l8; v < v1; v += 8) *reinterpret_cast<uint4 *>(out + (size_t)v * 16) = dec_run_vec<W>(sym, (v * 16u - m) % (uint32_t)W);
-          }
-        }
-      }
-    }
+    if (t == 0) S.ticket = atomicAdd(&cnt.ticket, 1u);
     __syncthreads();
-    // -- long operations: the whole CTA, or (huge) the whole grid in k_dec_big
+    const uint32_t c = S.ticket;
+    if (c >= nChunks) break;
+    const uint32_t c0 = c * DEC_CB;
+    const uint32_t availSC = clen - c0;
+    HSRLE_DBG(0x1000000u | c);
+    // ---- the chunk's first true token start: nearest anchor at or before the chunk inside its segment, then window-row hops
     {
-      const uint32_t nb = min(S.nBig, (uint32_t)DX_BIGCAP);
-      for (uint32_t i = 0; i < nb; i++)
+      const uint32_t gFirst = (c / DEC_SEG) * DEC_SEG;
+      if (warp == 0)
       {
-        const DecBigOp op = S.big[i];
-        for (uint32_t kk = t; kk < op.nv; kk += DX_T) dec_big_vec<W>(op, kk, in, out);
+        const uint32_t a = (gFirst + lane <= c) ? __ldcg(D.anchorAt + gFirst + lane) : 0u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, a != 0u);
+        if (lane == 0) { S.flag = m ? (31u - (uint32_t)__clz(m)) : 0xFFFFFFFFu; }
+        if (m && lane == (31 - __clz(m))) S.entry = a;
       }
       __syncthreads();
-      if (t == 0) S.nBig = 0;
+      const uint32_t ai = S.flag;
+      if (ai == 0xFFFFFFFFu) { if (t == 0) S.entry = POS_NONE; }
+      else if (gFirst + ai < c)
+      {
+        const uint32_t cA = gFirst + ai, nrow = c - cA;
+        for (uint32_t i = t; i < nrow * DEC_WIN; i += DX_T) rowStage[i] = __ldcg(D.chunkMap + (size_t)cA * DEC_WIN + i);
+        __syncthreads();
+        if (t == 0)
+        {
+          uint32_t x = S.entry, cc = cA, e = POS_NONE;
+          for (;;)
+          {
+            const uint32_t o = x - cc * DEC_CB;
+            if (o >= DEC_WIN) break;                               // entered outside the window: the chain's next chunk has its own anchor
+            x = rowStage[(cc - cA) * DEC_WIN + o];
+            if (x >= POS_SPECIAL) break;
+            const uint32_t c2 = x / DEC_CB;
+            if (c2 > c) break;
+            if (c2 == c) { e = x; break; }
+            cc = c2;
+          }
+          S.entry = e;
+        }
+      }
+      __syncthreads();
     }
-  }
-  dec_emit_done(D, &S.flag);
-}
-
-// grid-wide execution of the huge literal copies / run fills (a 1 GiB single-symbol frame is ONE run)
-constexpr uint32_t DBIG_PIECE = 1024;      // vectors per CTA step (16 KiB)
-template <int W>
-__global__ void __launch_bounds__(256) k_dec_big(const DecBufs D)
-{
-  const DecScalars &sc = *D.sc;
-  if (sc.status != ST_OK) return;
-  const uint32_t nMed = sc.nMed;
-  for (uint32_t i = blockIdx.x; i < nMed; i += gridDim.x)
-  {
-    const DecBigOp op = D.medList[i];
-    for (uint32_t kk = threadIdx.x; kk < op.nv; kk += 256) dec_big_vec<W>(op, kk, D.in, D.out);
-  }
-  const uint32_t nHuge = sc.nHuge;
-  for (uint32_t i = 0; i < nHuge; i++)
-  {
-    const DecBigOp op = D.hugeList[i];
-    const uint32_t nPieces = (op.nv + DBIG_PIECE - 1) / DBIG_PIECE;
-    for (uint32_t pc = blockIdx.x; pc < nPieces; pc += gridDim.x)
+    const uint32_t entry = S.entry;
+    const bool hasTok = entry < POS_SPECIAL && entry < clen;
+    HSRLE_DBG(0x2000000u | c);
+    // ---- image + sub-chunk rows by bulk copies (a chunk no token starts in -- it lies inside a long literal -- needs neither)
+    if (hasTok)
     {
-      const uint32_t k0 = pc * DBIG_PIECE, k1 = min(op.nv, k0 + DBIG_PIECE);
-      for (uint32_t kk = k0 + threadIdx.x; kk < k1; kk += 256) dec_big_vec<W>(op, kk, D.in, D.out);
+      if (t == 0)
+      {
+        fence_async_smem();
+        const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
+        mbar_expect_tx(&S.mbar[0], bytes + (uint32_t)sizeof(S.sub));
+        bulk_load(S.img, in + c0, bytes, &S.mbar[0]);
+        bulk_load(S.sub, D.subMap + (size_t)c * DEC_NSUB * DEC_WIN, (uint32_t)sizeof(S.sub), &S.mbar[0]);
+      }
+      if (!mbar_wait(&S.mbar[0], phase0)) cnt.emitBad = 0x200;
+      phase0 ^= 1u;
     }
+    HSRLE_DBG(0x3000000u | c);
+    // ---- sub-chunk entries: hops through the sub-chunk rows (a landing outside a window is walked token by token)
+    if (t < DEC_NSUB) { S.subEntry[t] = 0xFFFFFFFFu; }
+    __syncthreads();
+    if (t == 0 && hasTok)
+    {
+      uint32_t x = entry - c0;
+      while (x < DEC_CB && c0 + x < clen)
+      {
+        const uint32_t s = x / DEC_SB, os = x - s * DEC_SB;
+        if (S.subEntry[s] == 0xFFFFFFFFu) S.subEntry[s] = x;
+        uint32_t code;
+        if (os < DEC_WIN) code = S.sub[s][os];
+        else
+        {
+          uint32_t kind; TokF f;
+          const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
+          code = kind == TK_OK ? min(x + len, 0x7FFFu) : EX_BAD;   // (ends are handled by the walkers)
+        }
+        if (code >= EX_FAR) break;                                  // the chain ends or leaves the chunk far
+        x = code;
+      }
+    }
+    __syncthreads();
+    HSRLE_DBG(0x4000000u | c);
+    // ---- walk A (lanes 0..15 of warp 0): tokens, output bytes and symbol state of every sub-chunk
+    Agg mine = decagg_identity<K>();
+    if (warp == 0)
+    {
+      uint32_t myCnt = 0;
+      bool sawEnd = false, sawBad = false;
+      if (lane < DEC_NSUB && S.subEntry[lane] != 0xFFFFFFFFu)
+      {
+        uint32_t x = S.subEntry[lane];
+        const uint32_t subEnd = (lane + 1) * DEC_SB;
+        while (x < subEnd)
+        {
+          if (c0 + x >= clen) { sawBad = true; break; }
+          uint32_t kind; TokF f;
+          const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
+          if (kind == TK_BAD) { sawBad = true; break; }
+          const uint32_t lit = len - f.hdr;
+          // (the terminator proper -- range field 0 -- carries neither literal nor run; a zero count after the escape: last token,
+          //  its literal is still copied)
+          uint32_t runB = tok_run_bytes<W, BA, V>(f.cnt, single);
+          uint32_t litB = lit;
+          if (kind == TK_END) { runB = 0; if (len < f.hdr) litB = 0; }
+          mine.out += (uint64_t)litB + runB; myCnt++;
+          if (K) lutxf_touch(mine.xf, K, (int)f.idx, c0 + x + f.symOff);
+          else if (f.symOff != 0xFFu) mine.symPos = c0 + x + f.symOff;
+          if (kind == TK_END) { sawEnd = true; break; }
+          x = (len >= 0x10000u) ? 0x10000u : x + len;
+        }
+      }
+      mine.ntok = myCnt;
+      if (sawBad) cnt.emitBad = 1;
+      if (sawEnd) cnt.endSeen = 1;
+      // exclusive prefix over the 16 sub-chunks, chunk total in lane 31
+      Agg inc = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const Agg o = decagg_shfl_up<K>(inc, d);
+        if (lane >= d) inc = decagg_combine<K>(o, inc);
+      }
+      Agg ex = decagg_shfl_up<K>(inc, 1);
+      if (lane == 0) ex = decagg_identity<K>();
+      if (lane < DEC_NSUB) { S.subCnt[lane] = ex.ntok; S.subOut[lane] = ex.out; }
+      if (lane == 31) { S.subCnt[DEC_NSUB] = inc.ntok; S.subOut[DEC_NSUB] = inc.out; }
+      Agg tot = inc;                                                  // the chunk's total: lane 31's inclusive value
+      tot.out = __shfl_sync(0xFFFFFFFFu, inc.out, 31); tot.ntok = __shfl_sync(0xFFFFFFFFu, inc.ntok, 31); tot.symPos = __shfl_sync(0xFFFFFFFFu, inc.symPos, 31);
+      if (K)
+      {
+#pragma unroll
+        for (int i = 0; i < 7; i++) if (i < K) tot.xf.e[i] = __shfl_sync(0xFFFFFFFFu, inc.xf.e[i], 31);
+      }
+      HSRLE_DBG(0x5000000u | c);
+      // ---- publish the chunk's aggregate, look back for the exclusive prefix (decoupled look-back, 32 chunks per step)
+      if (lane == 0) { decagg_store<K>(&aggBuf[c], tot); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
+      Agg excl = decagg_identity<K>();
+      int64_t base = (int64_t)c - 1;
+      while (base >= 0)
+      {
+        const int64_t p = base - lane;
+        uint32_t fl = 2u;                                           // lanes before chunk 0 behave like an (identity) inclusive prefix
+        Agg v = decagg_identity<K>();
+        if (p >= 0)
+        {
+          uint32_t spin = 0;
+          do { fl = ld_volatile_u32(D.flagAgg + p); } while (fl == 0u && ++spin < (1u << 24));
+          if (fl == 0u) { cnt.emitBad = 0x400; fl = 2u; }            // (cannot happen: chunks are taken in order)
+          __threadfence();
+          v = decagg_load_cg<K>(fl == 2u ? &incBuf[p] : &aggBuf[p]);
+        }
+        const uint32_t incMask = __ballot_sync(0xFFFFFFFFu, fl == 2u);
+        const int j = incMask ? (__ffs(incMask) - 1) : 32;           // nearest inclusive prefix in this window
+        if (lane > j) v = decagg_identity<K>();
+        // ordered reduction: lane l ends with the combination of lanes l .. 31 (older lanes are the higher ones)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const Agg o = decagg_shfl_down<K>(v, d);
+          if (lane + d < 32) v = decagg_combine<K>(o, v);
+        }
+        Agg w0 = v;
+        w0.out = __shfl_sync(0xFFFFFFFFu, v.out, 0); w0.ntok = __shfl_sync(0xFFFFFFFFu, v.ntok, 0); w0.symPos = __shfl_sync(0xFFFFFFFFu, v.symPos, 0);
+        if (K)
+        {
+#pragma unroll
+          for (int i = 0; i < 7; i++) if (i < K) w0.xf.e[i] = __shfl_sync(0xFFFFFFFFu, v.xf.e[i], 0);
+        }
+        excl = decagg_combine<K>(w0, excl);
+        if (incMask) break;
+        base -= 32;
+      }
+      const Agg incl = decagg_combine<K>(excl, tot);
+      if (lane == 0)
+      {
+        decagg_store<K>(&incBuf[c], incl); __threadfence(); st_volatile_u32(D.flagAgg + c, 2u);
+        if (c == nChunks - 1) { cnt.outTotal = incl.out; cnt.nTok = incl.ntok; }
+        decagg_store<K>(&S.bc, excl);
+      }
+      // ---- symbol state at the start of every sub-chunk
+      {
+        const Agg before = decagg_combine<K>(excl, ex);              // everything before my sub-chunk
+        if (lane < DEC_NSUB)
+        {
+          if (K)
+          {
+            Lut l0; lut_init(l0, W);
+            Lut l1; lutxf_apply(before.xf, K, W, in, l0, l1);
+            S.subLut[K ? lane : 0] = l1;
+          }
+          else S.subSym[lane] = single ? (uint64_t)hs.singleSym : (before.symPos ? load_sym(in + before.symPos, W) : 0ull);
+        }
+      }
+    }
+    __syncthreads();
+    HSRLE_DBG(0x6000000u | c);
+    const uint32_t ntokChunk = S.subCnt[DEC_NSUB];
+    const uint64_t chunkOut0 = S.bc.out, chunkOutLen = S.subOut[DEC_NSUB];
+    // ---- expansion in passes of DEC_NSLOT tokens
+    for (uint32_t pass0 = 0; pass0 < ntokChunk; pass0 += DEC_NSLOT)
+    {
+      const uint32_t passN = min(DEC_NSLOT, ntokChunk - pass0);
+      __syncthreads();
+      if (t == 0) { S.nSkip = 0; }
+      // -- walk B: token records of the pass
+      if (warp == 0 && lane < DEC_NSUB && S.subEntry[lane] != 0xFFFFFFFFu)
+      {
+        const uint32_t k0 = S.subCnt[lane], k1 = (lane + 1 < DEC_NSUB) ? S.subCnt[lane + 1] : ntokChunk;
+        if (k1 > pass0 && k0 < pass0 + passN)
+        {
+          uint32_t x = S.subEntry[lane], k = k0;
+          uint64_t o = S.subOut[lane];
+          uint64_t symReg = K ? 0ull : S.subSym[lane];
+          Lut lut; if (K) lut = S.subLut[K ? lane : 0]; else lut_init(lut, W);
+          while (k < k1 && k < pass0 + passN)
+          {
+            uint32_t kind; TokF f;
+            const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
+            uint32_t runB = tok_run_bytes<W, BA, V>(f.cnt, single);
+            uint32_t litB = len - f.hdr;
+            if (kind == TK_END) { runB = 0; if (len < f.hdr) litB = 0; }
+            uint64_t sym;
+            if (K)
+            {
+              if (f.idx == (uint32_t)K) { uint64_t sv = 0; for (int i = 0; i < W; i++) sv |= (uint64_t)S.img[x + f.symOff + i] << (8 * i); lut_touch(lut, K, K, sv); }
+              else if (f.idx > 0) { const uint64_t sv = lut_get(lut, K, (int)f.idx); lut_touch(lut, K, (int)f.idx, sv); }
+              sym = lut.s[0];
+            }
+            else
+            {
+              if (f.symOff != 0xFFu) { uint64_t sv = 0; for (int i = 0; i < W; i++) sv |= (uint64_t)S.img[x + f.symOff + i] << (8 * i); symReg = sv; }
+              sym = symReg;
+            }
+            if (k >= pass0)
+            {
+              const uint32_t r = k - pass0;
+              S.rOut[r] = (uint32_t)min(o, (uint64_t)0xFFFFFFFFu); S.rLit[r] = litB; S.rRun[r] = runB; S.rSrc[r] = x + f.hdr; S.rSym[r] = sym;
+            }
+            o += (uint64_t)litB + runB; k++;
+            if (kind != TK_OK) break;
+            x += len;
+          }
+          if (k == pass0 + passN) S.rOut[passN] = (uint32_t)min(o, (uint64_t)0xFFFFFFFFu);     // sentinel: where the pass ends
+        }
+      }
+      __syncthreads();
+      HSRLE_DBG(0x7000000u | c);
+      // output range of the pass, absolute (never beyond the declared size)
+      const uint64_t pLo = min(chunkOut0 + S.rOut[0], (uint64_t)n);
+      const uint64_t pHi = min(chunkOut0 + ((pass0 + passN >= ntokChunk) ? chunkOutLen : (uint64_t)S.rOut[passN]), (uint64_t)n);
+      if (pHi <= pLo) continue;
+      const uint64_t T0 = pLo & ~(uint64_t)15;
+      const uint32_t nTiles = (uint32_t)((pHi - T0 + DEC_TILE - 1) / DEC_TILE);
+      // -- token parts that cover many whole tiles go to the grid
+      if (nTiles > DEC_HUGE_TILES)
+      {
+        for (uint32_t r = t; r < passN; r += DX_T)
+        {
+          const uint64_t a = chunkOut0 + S.rOut[r];
+          const uint64_t m = a + S.rLit[r], e = m + S.rRun[r];
+#pragma unroll 1
+          for (int part = 0; part < 2; part++)
+          {
+            const uint64_t pa = max(part ? m : a, pLo), pb = min(part ? e : m, pHi);
+            if (pb <= pa) continue;
+            const uint64_t kA = (pa - T0 + DEC_TILE - 1) / DEC_TILE, kB = (pb - T0) / DEC_TILE;
+            if (kB < kA + DEC_HUGE_TILES) continue;
+            const uint32_t slot = atomicAdd(&S.nSkip, 1u);
+            if (slot >= (uint32_t)DX_NSKIP) continue;
+            const uint32_t idx = atomicAdd(&cnt.nBig, 1u);
+            if (idx >= D.bigCap) { S.skipLo[slot] = 0; S.skipHi[slot] = 0; continue; }
+            S.skipLo[slot] = (uint32_t)kA; S.skipHi[slot] = (uint32_t)kB;
+            DecBigOp &op = D.bigList[idx];
+            op.dst = (uint32_t)(T0 + kA * DEC_TILE); op.len = (uint32_t)((kB - kA) * DEC_TILE); op.kind = (uint32_t)part; op.sym = S.rSym[r];
+            op.src = part ? (uint32_t)m : (uint32_t)(c0 + S.rSrc[r] + (T0 + kA * DEC_TILE - a));
+            op.next = 0;
+            __threadfence();
+            st_volatile_u32(&op.ready, 1u);
+          }
+        }
+        __syncthreads();
+      }
+      const uint32_t nSkip = min(S.nSkip, (uint32_t)DX_NSKIP);
+      for (uint32_t tk = 0; tk < nTiles; tk++)
+      {
+        { // inside a range handed to the grid?
+          uint32_t jump = 0;
+          for (uint32_t i = 0; i < nSkip; i++) if (tk >= S.skipLo[i] && tk < S.skipHi[i]) jump = S.skipHi[i];
+          if (jump) { tk = jump - 1; continue; }
+        }
+        HSRLE_DBG(0x8000000u | (tk & 0xFFFFFFu));
+        const uint64_t tb = T0 + (uint64_t)tk * DEC_TILE;
+        const uint64_t lo = max(tb, pLo), hi = min(tb + DEC_TILE, pHi);
+        __syncthreads();                                            // the previous tile is flushed
+        if (t == 0) S.nLong = 0;
+        __syncthreads();
+        // -- every token of the pass that overlaps the tile: short parts by the token's thread, long parts listed
+        for (uint32_t r = t; r < passN; r += DX_T)
+        {
+          const uint64_t a = chunkOut0 + S.rOut[r];
+          if (a >= hi) continue;
+          const uint64_t m = a + S.rLit[r], e = m + S.rRun[r];
+          if (e <= lo) continue;
+          { // literal part
+            const uint64_t pa = max(a, lo), pb = min(m, hi);
+            if (pb > pa)
+            {
+              const uint32_t len = (uint32_t)(pb - pa), d = (uint32_t)(pa - tb), rel = S.rSrc[r] + (uint32_t)(pa - a);
+              if (len <= DX_INLINE) { for (uint32_t i = 0; i < len; i++) S.tile[d + i] = (uint8_t)lit_byte(S.img, in, c0, rel + i); }
+              else { const uint32_t q = atomicAdd(&S.nLong, 1u); if (q < DX_LONGCAP) S.longList[q] = r * 2u; }
+            }
+          }
+          { // run part
+            const uint64_t pa = max(m, lo), pb = min(e, hi);
+            if (pb > pa)
+            {
+              const uint32_t len = (uint32_t)(pb - pa), d = (uint32_t)(pa - tb);
+              if (len <= DX_INLINE)
+              {
+                const uint64_t sym = S.rSym[r];
+                uint32_t ph = (uint32_t)((pa - m) % (uint32_t)W);
+                for (uint32_t i = 0; i < len; i++) { S.tile[d + i] = (uint8_t)run_byte<W>(sym, ph); ph = (ph + 1 == (uint32_t)W) ? 0u : ph + 1; }
+              }
+              else { const uint32_t q = atomicAdd(&S.nLong, 1u); if (q < DX_LONGCAP) S.longList[q] = r * 2u + 1u; }
+            }
+          }
+        }
+        __syncthreads();
+        // -- long parts: one warp each
+        {
+          const uint32_t nl = min(S.nLong, (uint32_t)DX_LONGCAP);
+          for (uint32_t q = warp; q < nl; q += DX_T / 32)
+          {
+            const uint32_t r = S.longList[q] >> 1, part = S.longList[q] & 1u;
+            const uint64_t a = chunkOut0 + S.rOut[r];
+            const uint64_t m = a + S.rLit[r], e = m + S.rRun[r];
+            if (!part)
+            {
+              const uint64_t pa = max(a, lo), pb = min(m, hi);
+              warp_copy(S.tile, (uint32_t)(pa - tb), (uint32_t)(pb - pa), S.img, in, c0, S.rSrc[r] + (uint32_t)(pa - a), lane);
+            }
+            else
+            {
+              const uint64_t pa = max(m, lo), pb = min(e, hi);
+              warp_fill<W>(S.tile, (uint32_t)(pa - tb), (uint32_t)(pb - pa), S.rSym[r], (uint32_t)((pa - m) % (uint32_t)W), lane);
+            }
+          }
+        }
+        __syncthreads();
+        // -- flush: whole vectors with 16-byte stores, the ragged ends (shared with the neighbouring chunks) byte-wise
+        {
+          const uint32_t b0 = (uint32_t)(lo - tb), b1 = (uint32_t)(hi - tb);
+          uint8_t *g = out + tb;
+          const uint32_t v0 = (b0 + 15u) >> 4, v1 = b1 >> 4;
+          for (uint32_t v = v0 + t; v < v1; v += DX_T) reinterpret_cast<uint4 *>(g)[v] = reinterpret_cast<const uint4 *>(S.tile)[v];
+          if (v1 >= v0)
+          {
+            if ((uint32_t)t < (v0 << 4) - b0) g[b0 + t] = S.tile[b0 + t];                 // head bytes [b0, 16 v0)
+            if ((uint32_t)t < b1 - (v1 << 4)) g[(v1 << 4) + t] = S.tile[(v1 << 4) + t];    // tail bytes [16 v1, b1)
+          }
+          else if (b0 + (uint32_t)t < b1) g[b0 + t] = S.tile[b0 + t];                      // both ends inside one vector
+        }
+      }
+    }
+    HSRLE_DBG(0x9000000u | c);
+    // ---- chunk done; the last one settles the status and the result
+    __syncthreads();
+    if (t == 0)
+    {
+      __threadfence();
+      if (atomicAdd(&cnt.chunksDone, 1u) == nChunks - 1)
+      {
+        __threadfence();
+        uint32_t status = ST_OK;
+        const uint32_t bad = ld_volatile_u32(&cnt.emitBad) | ld_volatile_u32(&cnt.chainBad), end = ld_volatile_u32(&cnt.endSeen);
+        const unsigned long long tot = ld_volatile_u64(&cnt.outTotal);
+        if (bad || !end || tot != (unsigned long long)n) status = ST_BADSTREAM;
+        D.dResult[0] = status == ST_OK ? n : 0; D.dResult[1] = status; D.dResult[2] = ld_volatile_u32(&cnt.nTok); D.dResult[3] = nChunks;
+        D.dResult[4] = clen; D.dResult[5] = hs.single; D.dResult[6] = ld_volatile_u32(&cnt.nBig); D.dResult[7] = bad;
+      }
+    }
+  }
+
+  // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken
+  for (uint32_t guard = 0;; guard++)
+  {
+    if (guard > (1u << 22)) { if (t == 0) cnt.emitBad = 0x500; break; }
+    HSRLE_DBG(0xA000000u | (guard & 0xFFFFFFu));
+    __syncthreads();
+    if (t == 0)
+    { // (one reader: the loop below must run the same number of times in every thread; "all done" is sampled first)
+      S.flag = (ld_volatile_u32(&cnt.chunksDone) >= nChunks) ? 1u : 0u;
+      __threadfence();
+      S.entry = min(ld_volatile_u32(&cnt.nBig), D.bigCap);
+    }
+    __syncthreads();
+    const bool allDone = S.flag != 0;
+    const uint32_t nb = S.entry;
+    __threadfence();
+    bool pending = false;
+    for (uint32_t i = 0; i < nb; i++)
+    {
+      DecBigOp &op = D.bigList[i];
+      __syncthreads();
+      if (t == 0) S.bcast = ld_volatile_u32(&op.ready);
+      __syncthreads();
+      if (!S.bcast) { pending = true; continue; }
+      __threadfence();
+      DecBigOp o;
+      o.sym = __ldcg(&op.sym); o.dst = __ldcg(&op.dst); o.len = __ldcg(&op.len); o.src = __ldcg(&op.src); o.kind = __ldcg(&op.kind);
+      const uint32_t np = (o.len + DEC_BIG_PIECE - 1) / DEC_BIG_PIECE;
+      for (;;)
+      {
+        __syncthreads();
+        if (t == 0) S.bcast = atomicAdd(&op.next, 1u);
+        __syncthreads();
+        const uint32_t k = S.bcast;
+        if (k >= np) break;
+        HSRLE_DBG(0xB000000u | (i << 16) | (k & 0xFFFFu));
+        dec_big_piece<W, K>(D, S, o, k * DEC_BIG_PIECE, min(DEC_BIG_PIECE, o.len - k * DEC_BIG_PIECE), phase0, phase1);
+      }
+    }
+    if (allDone && !pending) break;
+    if (!allDone) __nanosleep(500);
   }
 }
 

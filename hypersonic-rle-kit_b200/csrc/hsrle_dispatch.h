@@ -22,7 +22,6 @@ struct DecKernels
 {
   void (*map)(const DecBufs);
   void (*emit)(const DecBufs);
-  void (*big)(const DecBufs);
   size_t mapSmem, emitSmem;
   size_t aggBytes;        // sizeof(DecAgg<K>)
 };

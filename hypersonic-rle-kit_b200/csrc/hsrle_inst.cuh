@@ -30,7 +30,6 @@ template <int W, int BA, int V> static DecKernels make_dec_kernels()
   DecKernels k;
   k.map = &k_dec_map<W, BA, V>;
   k.emit = &k_dec_emit<W, BA, V>;
-  k.big = &k_dec_big<W>;
   k.mapSmem = sizeof(DecMapSmem);
   k.emitSmem = sizeof(DecEmitSmem<sp.K>);
   k.aggBytes = sizeof(DecAgg<sp.K>);
@@ -66,7 +65,7 @@ const DecKernels *HSRLE_CAT(dec_kernels_w, HSRLE_INST_W)()
   static bool init = false;
   if (!init)
   {
-    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, nullptr, 0, 0, 0 };
+    for (int i = 0; i < 8; i++) tab[i] = DecKernels{ nullptr, nullptr, 0, 0, 0 };
     constexpr int W = HSRLE_INST_W;
     if constexpr (W > 1)
     {
