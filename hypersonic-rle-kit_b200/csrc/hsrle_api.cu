@@ -186,8 +186,9 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.bigList = cv.take<DecBigOp>(D.bigCap);                                                  // (their `ready` words must start as 0)
   if (zeroBytes) *zeroBytes = cv.off;
   D.sc = cv.take<DecScalars>(1);
-  D.chunkMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WIN);
-  D.sufMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WIN);
+  D.chunkTab = cv.take<uint16_t>((size_t)D.nChunks * DEC_CB);
+  D.sufMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WINC);
+  D.chunkEntry = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.subMap = cv.take<uint16_t>((size_t)D.nChunks * DEC_NSUB * DEC_WIN);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes);
   return cv.off + 256;

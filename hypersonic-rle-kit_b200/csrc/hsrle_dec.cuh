@@ -35,8 +35,9 @@ namespace hsrle {
 constexpr uint32_t DEC_CB = 16384;        // chunk: stream bytes per CTA step
 constexpr uint32_t DEC_SB = 1024;         // sub-chunk: the unit one lane walks in K2
 constexpr int DEC_NSUB = (int)(DEC_CB / DEC_SB);
-constexpr uint32_t DEC_WIN = 288;         // entry window: a token with a 1-byte range field ends < 8 + 11 + 254 bytes after its start
-constexpr uint32_t DEC_SEG = 32;          // chunks per segment
+constexpr uint32_t DEC_WIN = 288;         // entry window of a sub-chunk: a token with a 1-byte range field ends < 8 + 11 + 254 bytes after its start
+constexpr uint32_t DEC_WINC = 512;        // entry window of a chunk in the composed segment rows (entries beyond it take the chunk's own table)
+constexpr uint32_t DEC_SEG = 16;          // chunks per segment
 constexpr uint32_t DEC_IMG_PAD = 512;     // stream bytes loaded after the chunk (token heads and short literals that straddle its end)
 constexpr uint32_t DEC_TILE = 16384;      // output image bytes per expansion step
 constexpr uint32_t DEC_NSLOT = 1024;      // token records per expansion pass
@@ -191,9 +192,10 @@ struct DecBufs
   uint32_t *segCount;       // [nSeg]    chunks of the segment that published their rows
   uint32_t *anchorAt;       // [nChunks] position of the first true token start the resolver saw in the chunk (0: none)
   uint32_t *flagAgg;        // [nChunks] look-back: 1 = aggregate published, 2 = inclusive prefix published   ... to here
-  uint32_t *chunkMap;       // [nChunks][DEC_WIN] absolute exit of the chunk when entered at window offset w
-  uint32_t *sufMap;         // [nChunks][DEC_WIN] ... of the SEGMENT (or the first out-of-window landing inside it)
+  uint16_t *chunkTab;       // [nChunks][DEC_CB]  exit code of the chunk for EVERY entry offset (read at the few offsets the chain visits)
+  uint32_t *sufMap;         // [nChunks][DEC_WINC] absolute exit of the SEGMENT (or the first out-of-window landing inside it) per window offset
   uint16_t *subMap;         // [nChunks][DEC_NSUB][DEC_WIN] exit codes of the sub-chunks
+  uint32_t *chunkEntry;     // [nChunks] first true token start of the chunk (POS_NONE: none) -- written by the resolver, read by K2
   void *aggBuf, *incBuf;    // [nChunks] DecAgg<K>: per-chunk totals / inclusive prefixes
   DecBigOp *bigList;
   uint32_t bigCap;

@@ -170,7 +170,7 @@ constexpr uint32_t DEC_HB = 64;            // the unit one thread sweeps
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
 constexpr uint32_t DEC_EXH_ELEMS = DEC_CB + (DEC_CB / 64 + 1) * 2;
 constexpr uint32_t DEC_IMG_BYTES = DEC_CB + DEC_IMG_PAD + 64;
-constexpr uint32_t DM_STAGE_ROWS = 40;     // segment rows the resolver stages at a time
+constexpr uint32_t DM_STAGE_ROWS = 20;     // segment rows the resolver stages at a time
 
 struct DecMapSmem
 {
@@ -179,8 +179,8 @@ struct DecMapSmem
   alignas(8) unsigned long long mbar;
   uint32_t flag, pos, gBase, done;
 };
-static_assert(DEC_IMG_BYTES % 16 == 0 && DEC_IMG_BYTES + DEC_EXH_ELEMS * 2 >= DM_STAGE_ROWS * DEC_WIN * 4, "rows fit the image + table area");
-static_assert(DEC_SEG * DEC_WIN * 4 <= DEC_IMG_BYTES + DEC_EXH_ELEMS * 2, "segment rows fit");
+static_assert(DEC_IMG_BYTES % 16 == 0 && DEC_IMG_BYTES + DEC_EXH_ELEMS * 2 >= DM_STAGE_ROWS * DEC_WINC * 4, "rows fit the image + table area");
+static_assert(DEC_SEG * DEC_WINC * 4 <= DEC_IMG_BYTES + DEC_EXH_ELEMS * 2, "segment rows fit");
 
 // absolute position (or POS_END / POS_BAD) a final exit code stands for; far-jumping tokens are parsed again from the image
 template <int W, int BA, int V>
@@ -194,11 +194,24 @@ __device__ __forceinline__ uint32_t dec_code_abs(uint32_t code, uint32_t c0, con
   return kind == TK_OK ? c0 + p + len : (kind == TK_END ? POS_END : POS_BAD);
 }
 
+// the same for a code read back from the chunk table in global memory: far-jumping tokens are parsed from the stream
+template <int W, int BA, int V>
+__device__ __forceinline__ uint32_t dec_tab_abs(const DecBufs &D, uint32_t code, uint32_t c0, bool single, uint32_t clen)
+{
+  constexpr Spec sp = make_spec(W, BA, V);
+  if (code < EX_FAR) return c0 + code;
+  if (code < EX_FARP) return code == EX_END ? POS_END : POS_BAD;
+  const uint32_t tp = c0 + (code & 0x3FFFu);
+  Tok tk; dec_parse(sp, single, D.in + tp, (uint64_t)clen - tp, tk);
+  if (!tk.valid) return POS_BAD;
+  if (tk.last) return POS_END;
+  return tp + tk.hdrLen + tk.litLen;                                  // <= clen (the token fits)
+}
+
 // the resolver: follows the true chain from the stream start, leaves an anchor in every chunk it visits
 template <int W, int BA, int V>
 __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &S, uint32_t *rows)
 {
-  constexpr Spec sp = make_spec(W, BA, V);
   const int t = threadIdx.x;
   const uint32_t clen = hs.clen;
   const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB, nSeg = (nChunks + DEC_SEG - 1) / DEC_SEG;
@@ -211,10 +224,10 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
     const uint32_t g0 = S.gBase;
     // stage the rows of the first chunks of segments [g0, g0 + DM_STAGE_ROWS)
     const uint32_t nr = min((uint32_t)DM_STAGE_ROWS, nSeg - g0);
-    for (uint32_t i = t; i < nr * DEC_WIN; i += DM_T)
+    for (uint32_t i = t; i < nr * DEC_WINC; i += DM_T)
     {
-      const uint32_t g = g0 + i / DEC_WIN, w = i % DEC_WIN;
-      rows[i] = __ldcg(D.sufMap + (size_t)g * DEC_SEG * DEC_WIN + w);
+      const uint32_t g = g0 + i / DEC_WINC, w = i % DEC_WINC;
+      rows[i] = __ldcg(D.sufMap + (size_t)g * DEC_SEG * DEC_WINC + w);
     }
     __syncthreads();
     if (t == 0)
@@ -223,37 +236,18 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
       bool fin = false;
       for (uint32_t guard = 0;; guard++)
       {
-        if (guard > (1u << 22)) { pos = POS_BAD; fin = true; D.cnt->chainBad = 0x600; break; }   // (every step advances by at least one token: never reached)
+        if (guard > (1u << 24)) { pos = POS_BAD; fin = true; D.cnt->chainBad = 0x600; break; }   // (every step advances by at least one chunk: never reached)
         if (pos >= POS_SPECIAL) { fin = true; break; }
         if (pos >= clen) { pos = POS_BAD; fin = true; break; }
         const uint32_t c = pos / DEC_CB, o = pos - c * DEC_CB, g = c / DEC_SEG;
         if (g >= g0 + nr) break;                                    // beyond the staged rows: stage again from there
         if (c != lastAnchor) { D.anchorAt[c] = pos; lastAnchor = c; }
-        if (o < DEC_WIN)
+        if (o < DEC_WINC)
         {
-          if (c == g * DEC_SEG && g >= g0) pos = rows[(g - g0) * DEC_WIN + o];
-          else pos = __ldcg(D.sufMap + (size_t)c * DEC_WIN + o);
+          if (c == g * DEC_SEG) pos = rows[(g - g0) * DEC_WINC + o];
+          else pos = __ldcg(D.sufMap + (size_t)c * DEC_WINC + o);
         }
-        else
-        { // outside every chunk window (after a long literal): sub-chunk row if inside a sub-chunk window, else parse the token
-          const uint32_t s = o / DEC_SB, os = o - s * DEC_SB;
-          uint32_t tp = pos;                                         // position of the token to parse (if any)
-          bool parse = true;
-          if (os < DEC_WIN)
-          {
-            const uint32_t code = __ldcg(D.subMap + ((size_t)c * DEC_NSUB + s) * DEC_WIN + os);
-            if (code < EX_FAR) { pos = c * DEC_CB + code; parse = false; }
-            else if (code < EX_FARP) { pos = code == EX_END ? POS_END : POS_BAD; parse = false; }
-            else tp = c * DEC_CB + (code & 0x3FFFu);
-          }
-          if (parse)
-          {
-            Tok tk; dec_parse(sp, single, D.in + tp, (uint64_t)clen - tp, tk);
-            if (!tk.valid) pos = POS_BAD;
-            else if (tk.last) pos = POS_END;
-            else pos = tp + tk.hdrLen + tk.litLen;                   // <= clen (the token fits)
-          }
-        }
+        else pos = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + o), c * DEC_CB, single, clen);   // after a long literal
       }
       S.pos = pos;
       if (fin) S.done = 1; else S.gBase = pos / DEC_CB / DEC_SEG;
@@ -262,6 +256,26 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
     if (S.done) break;
   }
   if (t == 0 && S.pos != POS_END) D.cnt->chainBad = 1;
+  __threadfence();
+  __syncthreads();
+  // every chunk's first true token start: one thread per segment walks its chunks through the chunk tables from the anchors
+  for (uint32_t g = t; g < nSeg; g += DM_T)
+  {
+    const uint32_t cFirst = g * DEC_SEG, cEnd = min(cFirst + DEC_SEG, nChunks);
+    uint32_t x = POS_NONE;                                           // chain position (absolute), once an anchor was met
+    for (uint32_t c = cFirst; c < cEnd; c++)
+    {
+      const uint32_t a = __ldcg(D.anchorAt + c);
+      if (a) x = a;
+      uint32_t e = POS_NONE;
+      if (x < POS_SPECIAL && x / DEC_CB == c)
+      {
+        e = x;
+        x = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + (x - c * DEC_CB)), c * DEC_CB, single, clen);
+      }
+      D.chunkEntry[c] = e;
+    }
+  }
 }
 
 template <int W, int BA, int V>
@@ -318,7 +332,9 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   __syncthreads();
   if (skipped)
   {
-    for (uint32_t w = t; w < DEC_WIN; w += DM_T) D.chunkMap[(size_t)c * DEC_WIN + w] = POS_BAD;
+    const uint32_t bad2 = EX_BAD | (EX_BAD << 16);
+    uint4 *dst = reinterpret_cast<uint4 *>(D.chunkTab + (size_t)c * DEC_CB);
+    for (uint32_t q = t; q < DEC_CB / 8; q += DM_T) dst[q] = make_uint4(bad2, bad2, bad2, bad2);
   }
   else
   {
@@ -365,40 +381,65 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     }
     __syncthreads();
     //      B2: block sizes 128, 256, 512: the lower half of every block takes the (final) entry of the upper half it exits into
-#pragma unroll 1
-    for (uint32_t half = DEC_HB; half <= 256; half <<= 1)
+#pragma unroll
+    for (int lg = 6; lg <= 8; lg++)
     {
+      constexpr uint32_t one = 1u;
+      const uint32_t half = one << lg;
+#pragma unroll 4
       for (uint32_t i = t; i < DEC_CB / 2; i += DM_T)
       {
-        const uint32_t blk = i / half, p = blk * 2 * half + (i - blk * half);
+        const uint32_t blk = i >> lg, p = (blk << (lg + 1)) + (i & (half - 1));
         const uint32_t code = ex[skew16h(p)];
-        if (code < (blk + 1) * 2 * half) ex[skew16h(p)] = ex[skew16h(code)];
+        if (code < ((blk + 1) << (lg + 1))) ex[skew16h(p)] = ex[skew16h(code)];
       }
       __syncthreads();
     }
     //      B3: sub-chunk level, window offsets only (after B2 every entry of a 512-byte block leaves the block)
-    for (uint32_t i = t; i < DEC_NSUB * DEC_WIN; i += DM_T)
+#pragma unroll 4
+    for (uint32_t s = 0; s < (uint32_t)DEC_NSUB; s++)
     {
-      const uint32_t s = i / DEC_WIN, p = s * DEC_SB + (i - s * DEC_WIN);
-      const uint32_t code = ex[skew16h(p)];
-      if (code < (s + 1) * DEC_SB) ex[skew16h(p)] = ex[skew16h(code)];
+      for (uint32_t w = t; w < DEC_WIN; w += DM_T)
+      {
+        const uint32_t p = s * DEC_SB + w;
+        const uint32_t code = ex[skew16h(p)];
+        if (code < (s + 1) * DEC_SB) ex[skew16h(p)] = ex[skew16h(code)];
+      }
     }
     __syncthreads();
     // ---- the sub-chunk rows (K2 walks the sub-chunks from them)
     {
       uint32_t *dst = reinterpret_cast<uint32_t *>(D.subMap + (size_t)c * DEC_NSUB * DEC_WIN);
-      for (uint32_t i = t; i < DEC_NSUB * DEC_WIN / 2; i += DM_T)
+#pragma unroll 4
+      for (uint32_t s = 0; s < (uint32_t)DEC_NSUB; s++)
       {
-        const uint32_t s = i / (DEC_WIN / 2), p = s * DEC_SB + (i - s * (DEC_WIN / 2)) * 2;
-        dst[i] = (uint32_t)ex[skew16h(p)] | ((uint32_t)ex[skew16h(p + 1)] << 16);
+        if (t < DEC_WIN / 2)
+        {
+          const uint32_t p = s * DEC_SB + 2u * t;
+          dst[s * (DEC_WIN / 2) + t] = (uint32_t)ex[skew16h(p)] | ((uint32_t)ex[skew16h(p + 1)] << 16);
+        }
       }
     }
-    // ---- the chunk row: chase through the sub-chunk entries (in-window hops take one look-up per sub-chunk)
-    for (uint32_t w = t; w < DEC_WIN; w += DM_T)
+    __syncthreads();
+    // ---- chunk level, in place, for EVERY offset: 512-byte blocks in reverse order (a code below the end of the chunk points into a
+    //      later block, final already) -- one look-up per offset
+    for (int b = (int)(DEC_CB / 512) - 2; b >= 0; b--)
     {
-      uint32_t x = ex[skew16h(w)];
-      while (x < DEC_CB) x = ex[skew16h(x)];
-      D.chunkMap[(size_t)c * DEC_WIN + w] = dec_code_abs<W, BA, V>(x, c0, S.img, single, availSC);
+      for (uint32_t p = (uint32_t)b * 512 + t; p < (uint32_t)(b + 1) * 512; p += DM_T)
+      {
+        const uint32_t code = ex[skew16h(p)];
+        if (code < DEC_CB) ex[skew16h(p)] = ex[skew16h(code)];
+      }
+      __syncthreads();
+    }
+    // ---- the chunk table (eight entries per 16-byte store)
+    {
+      uint4 *dst = reinterpret_cast<uint4 *>(D.chunkTab + (size_t)c * DEC_CB);
+      for (uint32_t q = t * 8; q < DEC_CB; q += DM_T * 8)
+      {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(ex + skew16h(q));
+        dst[q >> 3] = make_uint4(src[0], src[1], src[2], src[3]);
+      }
     }
   }
   // ---- the last chunk of a segment composes the segment's rows; the last segment resolves the chain
@@ -410,23 +451,27 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   if (!S.flag) return;
   __threadfence();
   {
-    for (uint32_t i = t; i < nHere * DEC_WIN; i += DM_T) rows[i] = __ldcg(D.chunkMap + (size_t)cFirst * DEC_WIN + i);
+    for (uint32_t i = t; i < nHere * DEC_WINC; i += DM_T)
+    {
+      const uint32_t ci = cFirst + i / DEC_WINC, w = i % DEC_WINC;
+      rows[i] = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)ci * DEC_CB + w), ci * DEC_CB, single, clen);
+    }
     __syncthreads();
     const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_CB;
     for (int i = (int)nHere - 2; i >= 0; i--)
     {
-      for (uint32_t w = t; w < DEC_WIN; w += DM_T)
+      for (uint32_t w = t; w < DEC_WINC; w += DM_T)
       {
-        const uint32_t x = rows[i * DEC_WIN + w];
+        const uint32_t x = rows[i * DEC_WINC + w];
         if (x < POS_SPECIAL && (uint64_t)x < segEnd)
         {
           const uint32_t c2 = x / DEC_CB, off = x - c2 * DEC_CB;
-          if (off < DEC_WIN) rows[i * DEC_WIN + w] = rows[(c2 - cFirst) * DEC_WIN + off];      // a later chunk of the segment: final already
+          if (off < DEC_WINC) rows[i * DEC_WINC + w] = rows[(c2 - cFirst) * DEC_WINC + off];      // a later chunk of the segment: final already
         }
       }
       __syncthreads();
     }
-    for (uint32_t i = t; i < nHere * DEC_WIN; i += DM_T) D.sufMap[(size_t)cFirst * DEC_WIN + i] = rows[i];
+    for (uint32_t i = t; i < nHere * DEC_WINC; i += DM_T) D.sufMap[(size_t)cFirst * DEC_WINC + i] = rows[i];
   }
   __threadfence();
   __syncthreads();
@@ -444,28 +489,37 @@ constexpr uint32_t DX_INLINE = 64;          // token parts up to this many bytes
 constexpr int DX_NSKIP = 16;                // whole-tile ranges of a chunk handed to the grid
 constexpr uint32_t DX_LONGCAP = DEC_TILE / DX_INLINE * 2 + 8;
 
+constexpr uint32_t DX_POSCAP = DEC_SB / 2;  // tokens that can start in one sub-chunk (the shortest token has two bytes)
+
 template <int K> struct DecEmitSmem
 {
   alignas(16) uint8_t img[DEC_IMG_BYTES];           // chunk image + pad (bulk-copy destination)
-  alignas(16) uint8_t tile[DEC_TILE];                // output image of one expansion step (also: staging of chunk rows / bulk literal source)
-  uint64_t rSym[DEC_NSLOT];                           // token records of an expansion pass: run symbol (first period) ...
-  uint32_t rOut[DEC_NSLOT + 4];                       // ... output offset relative to the chunk's first output byte (+ sentinel) ...
-  uint32_t rLit[DEC_NSLOT];                           // ... literal bytes ...
-  uint32_t rRun[DEC_NSLOT];                           // ... run bytes ...
-  uint32_t rSrc[DEC_NSLOT];                           // ... literal source relative to the chunk start
-  alignas(16) uint16_t sub[DEC_NSUB][DEC_WIN];        // sub-chunk rows of the chunk
+  alignas(16) uint8_t tile[DEC_TILE];                // output image of one expansion step; before that: the chunk's sub-chunk rows
+  uint16_t pos[DEC_NSUB][DX_POSCAP];                  // token starts of every sub-chunk (chunk-relative), written by the walkers
+  uint16_t ref[K ? DEC_NSUB : 1][K ? DX_POSCAP : 1];  // K > 0: per token, where its symbol comes from: < 8 table slot at the start of the
+                                                      //        sub-chunk, else 8 + chunk-relative position of an explicit symbol
+  uint32_t rOut[DEC_NSLOT + 4];                       // token records of an expansion group: output offset relative to the chunk's first
+  uint32_t rLit[DEC_NSLOT];                           //   output byte (+ sentinel), literal bytes,
+  uint32_t rRun[DEC_NSLOT];                           //   run bytes,
+  uint16_t rSrc[DEC_NSLOT];                           //   literal source (chunk-relative),
+  uint16_t rSymI[DEC_NSLOT];                          //   symbol: K == 0 chunk-relative position of the governing explicit symbol (0xFFFF: the
+  uint8_t rSub[DEC_NSLOT];                            //   chunk's incoming one); K > 0 the token's `ref`; and the token's sub-chunk
   uint32_t subEntry[DEC_NSUB];
   uint32_t subCnt[DEC_NSUB + 1];                      // tokens per sub-chunk -> exclusive prefix
-  uint64_t subOut[DEC_NSUB + 1];                      // output bytes per sub-chunk -> exclusive prefix (relative to the chunk)
-  uint64_t subSym[DEC_NSUB];                          // K == 0: symbol register at the start of the sub-chunk
+  uint32_t subEnd[DEC_NSUB];                          // 1: the sub-chunk's walker met the last token, 2: an unparsable one
+  LutXf subXf[K ? DEC_NSUB : 1];                      // K > 0: table transform of every sub-chunk
   Lut subLut[K ? DEC_NSUB : 1];                       // K > 0: table at the start of the sub-chunk
   DecAgg<K> bc;                                       // look-back result
+  unsigned long long warpSum[DX_T / 32 + 1];          // block scans: output bytes ...
+  uint32_t warpSymI[DX_T / 32 + 1];                   // ... and last explicit symbol
+  unsigned long long sumOut;                          // output bytes of the chunk / of the groups before the current one
+  uint32_t sumSym;                                    // K == 0: chunk-relative position + 1 of the last explicit symbol so far (0: none)
+  uint64_t inSym;                                     // K == 0: symbol register at the start of the chunk
   uint32_t longList[DX_LONGCAP];
   uint32_t skipLo[DX_NSKIP], skipHi[DX_NSKIP];
   alignas(8) unsigned long long mbar[2];
   uint32_t nLong, nSkip, ticket, entry, flag, bcast;
 };
-static_assert(DEC_TILE + DEC_NSLOT * 24 >= (DEC_SEG - 1) * DEC_WIN * 4, "chunk rows fit the tile + record area");
 
 // field-wise helpers (K == 0 aggregates carry no LUT transform: nothing of it is moved)
 template <int K> __device__ __forceinline__ DecAgg<K> decagg_shfl_down(const DecAgg<K> &v, int d)
@@ -595,6 +649,95 @@ __device__ void dec_big_piece(const DecBufs &D, DecEmitSmem<K> &S, const DecBigO
   for (uint32_t v = t; v < (len >> 4); v += DX_T) reinterpret_cast<uint4 *>(out)[v] = dec_lit_vec(D.in, src0 + 16u * v);
 }
 
+// length of the token at x for the walkers: the common shapes (no escaped count / range field) from two or three bytes of the
+// image, everything else through the general parse.  Returns the kind; len as toklen.
+template <int W, int BA, int V>
+__device__ __forceinline__ uint32_t tok_walk_len(const uint8_t *img, uint32_t x, bool single, uint32_t avail, uint32_t &len, uint32_t &idx)
+{
+  constexpr Spec sp = make_spec(W, BA, V);
+  constexpr int K = sp.K;
+  idx = 0;
+  if constexpr (K != 0)
+  {
+    constexpr int RB = (K == 3) ? 7 : 6;
+    const uint32_t head = (uint32_t)img[x] | ((uint32_t)img[x + 1] << 8);
+    idx = head >> (K == 3 ? 14 : 13);
+    const uint32_t c7 = (head >> RB) & 0x7F, r = head & ((1u << RB) - 1u);
+    const uint32_t hdr = 2u + (idx == (uint32_t)K ? (uint32_t)W : 0u);
+    if (c7 >= 2 && r >= 2 && hdr <= avail && r - 2 <= avail - hdr) { len = hdr + r - 2; return TK_OK; }
+  }
+  else if (V == V_PLAIN || (W == 1 && single))
+  {
+    const uint32_t S = (W == 1 && single) ? 0u : (uint32_t)W;
+    const uint32_t c = img[x + S], r = img[x + S + 1];
+    if (c != 0 && r != 0 && S + 2 <= avail && r - 1 <= avail - (S + 2)) { len = S + 1 + r; return TK_OK; }
+  }
+  else
+  {
+    const uint32_t b0 = img[x];
+    const uint32_t o = 1u + ((b0 & 0x80u) ? 0u : (uint32_t)W);
+    const uint32_t r = img[x + o];
+    if ((b0 & 0x7Fu) != 0)
+    {
+      if (sp.rng7) { if ((r & 1u) == 0 && r >= 2 && o + 1 <= avail && (r >> 1) - 1 <= avail - (o + 1)) { len = o + (r >> 1); return TK_OK; } }
+      else if (r != 0 && o + 1 <= avail && r - 1 <= avail - (o + 1)) { len = o + r; return TK_OK; }
+    }
+  }
+  uint32_t kind; TokF f;
+  len = toklen_at<W, BA, V>(img, x, single, avail, kind, f);
+  idx = f.idx;
+  return kind;
+}
+
+// W bytes of the image at p as a symbol
+template <int W> __device__ __forceinline__ uint64_t img_sym(const uint8_t *img, uint32_t p)
+{
+  uint64_t v = 0;
+#pragma unroll
+  for (int i = 0; i < W; i++) v |= (uint64_t)img[p + i] << (8 * i);
+  return v;
+}
+
+// a short literal part by one thread: bytes up to the next word of the image, words, bytes
+__device__ __forceinline__ void thread_copy(uint8_t *tile, uint32_t d, uint32_t len, const uint8_t *img, const uint8_t *__restrict__ in, uint32_t c0, uint32_t rel)
+{
+  if (rel + len + 4 > DEC_CB + DEC_IMG_PAD) { for (uint32_t i = 0; i < len; i++) tile[d + i] = (uint8_t)lit_byte(img, in, c0, rel + i); return; }
+  uint32_t i = 0;
+  const uint32_t head = min(len, (4u - (d & 3u)) & 3u);
+  for (; i < head; i++) tile[d + i] = img[rel + i];
+  const uint32_t nw = (len - i) >> 2;
+  if (nw)
+  {
+    const uint32_t r = rel + i, sh = (r & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(img) + (r >> 2);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(tile + d + i);
+    uint32_t lo = sw[0];
+    for (uint32_t k = 0; k < nw; k++) { const uint32_t hi = sw[k + 1]; dw[k] = __funnelshift_r(lo, hi, sh); lo = hi; }
+    i += nw << 2;
+  }
+  for (; i < len; i++) tile[d + i] = img[rel + i];
+}
+// a short run part by one thread
+template <int W> __device__ __forceinline__ void thread_fill(uint8_t *tile, uint32_t d, uint32_t len, uint64_t sym, uint32_t ph)
+{
+  if constexpr (W == 1)
+  {
+    const uint32_t b = (uint32_t)sym & 0xFFu, w = b * 0x01010101u;
+    uint32_t i = 0;
+    const uint32_t head = min(len, (4u - (d & 3u)) & 3u);
+    for (; i < head; i++) tile[d + i] = (uint8_t)b;
+    const uint32_t nw = (len - i) >> 2;
+    uint32_t *dw = reinterpret_cast<uint32_t *>(tile + d + i);
+    for (uint32_t k = 0; k < nw; k++) dw[k] = w;
+    i += nw << 2;
+    for (; i < len; i++) tile[d + i] = (uint8_t)b;
+  }
+  else
+  {
+    for (uint32_t i = 0; i < len; i++) { tile[d + i] = (uint8_t)run_byte<W>(sym, ph); ph = (ph + 1 == (uint32_t)W) ? 0u : ph + 1; }
+  }
+}
+
 template <int W, int BA, int V>
 __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
 {
@@ -604,6 +747,9 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   using Smem = DecEmitSmem<K>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
   Smem &S = *reinterpret_cast<Smem *>(smemRaw);
+  uint16_t (*const subRows)[DEC_WIN] = reinterpret_cast<uint16_t (*)[DEC_WIN]>(S.tile);     // the sub-chunk rows live in the tile buffer until the expansion
+  constexpr uint32_t SUBROW_BYTES = DEC_NSUB * DEC_WIN * 2;
+  static_assert(SUBROW_BYTES <= DEC_TILE, "sub-chunk rows fit the tile buffer");
   const DecScalars hs = *D.sc;
   DecCounters &cnt = *D.cnt;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -618,62 +764,48 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   const uint8_t *__restrict__ in = D.in;
   uint8_t *__restrict__ out = D.out;
   Agg *aggBuf = reinterpret_cast<Agg *>(D.aggBuf), *incBuf = reinterpret_cast<Agg *>(D.incBuf);
-  uint32_t *const rowStage = reinterpret_cast<uint32_t *>(S.tile);   // chunk rows for the entry derivation (tile + record area)
   if (t == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); }
   uint32_t phase0 = 0, phase1 = 0;
   __syncthreads();
 #define HSRLE_DBG(code) do { if (D.dbg && t == 0) { *((volatile uint32_t *)D.dbg + blockIdx.x) = (uint32_t)(code); __threadfence_system(); } } while (0)
 
+  // block-wide exclusive scan of (output bytes, last explicit symbol) over the threads; totals returned in (totOut, totSym)
+  auto block_scan = [&](unsigned long long myOut, uint32_t mySym, unsigned long long &exOut, uint32_t &exSym, unsigned long long &totOut, uint32_t &totSym)
+  {
+    unsigned long long io = myOut; uint32_t is = mySym;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, io, d); const uint32_t q = __shfl_up_sync(0xFFFFFFFFu, is, d);
+      if (lane >= d) { io += o; is = max(is, q); }
+    }
+    if (lane == 31) { S.warpSum[warp] = io; S.warpSymI[warp] = is; }
+    unsigned long long eo = __shfl_up_sync(0xFFFFFFFFu, io, 1); uint32_t es = __shfl_up_sync(0xFFFFFFFFu, is, 1);
+    if (lane == 0) { eo = 0; es = 0; }
+    __syncthreads();
+    unsigned long long po = 0, to = 0; uint32_t ps = 0, tsy = 0;
+#pragma unroll
+    for (int w = 0; w < DX_T / 32; w++) { const unsigned long long x = S.warpSum[w]; const uint32_t y = S.warpSymI[w]; if (w < warp) { po += x; ps = max(ps, y); } to += x; tsy = max(tsy, y); }
+    __syncthreads();
+    exOut = po + eo; exSym = max(ps, es); totOut = to; totSym = tsy;
+  };
+
   for (;;)
   {
     __syncthreads();
-    if (t == 0) S.ticket = atomicAdd(&cnt.ticket, 1u);
+    if (t == 0) { S.ticket = atomicAdd(&cnt.ticket, 1u); }
     __syncthreads();
     const uint32_t c = S.ticket;
     if (c >= nChunks) break;
     const uint32_t c0 = c * DEC_CB;
     const uint32_t availSC = clen - c0;
     HSRLE_DBG(0x1000000u | c);
-    // ---- the chunk's first true token start: nearest anchor at or before the chunk inside its segment, then window-row hops
-    {
-      const uint32_t gFirst = (c / DEC_SEG) * DEC_SEG;
-      if (warp == 0)
-      {
-        const uint32_t a = (gFirst + lane <= c) ? __ldcg(D.anchorAt + gFirst + lane) : 0u;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, a != 0u);
-        if (lane == 0) { S.flag = m ? (31u - (uint32_t)__clz(m)) : 0xFFFFFFFFu; }
-        if (m && lane == (31 - __clz(m))) S.entry = a;
-      }
-      __syncthreads();
-      const uint32_t ai = S.flag;
-      if (ai == 0xFFFFFFFFu) { if (t == 0) S.entry = POS_NONE; }
-      else if (gFirst + ai < c)
-      {
-        const uint32_t cA = gFirst + ai, nrow = c - cA;
-        for (uint32_t i = t; i < nrow * DEC_WIN; i += DX_T) rowStage[i] = __ldcg(D.chunkMap + (size_t)cA * DEC_WIN + i);
-        __syncthreads();
-        if (t == 0)
-        {
-          uint32_t x = S.entry, cc = cA, e = POS_NONE;
-          for (;;)
-          {
-            const uint32_t o = x - cc * DEC_CB;
-            if (o >= DEC_WIN) break;                               // entered outside the window: the chain's next chunk has its own anchor
-            x = rowStage[(cc - cA) * DEC_WIN + o];
-            if (x >= POS_SPECIAL) break;
-            const uint32_t c2 = x / DEC_CB;
-            if (c2 > c) break;
-            if (c2 == c) { e = x; break; }
-            cc = c2;
-          }
-          S.entry = e;
-        }
-      }
-      __syncthreads();
-    }
+    // ---- the chunk's first true token start (K1's resolver)
+    if (t == 0) S.entry = __ldcg(D.chunkEntry + c);
+    if (t < DEC_NSUB) { S.subEntry[t] = 0xFFFFFFFFu; S.subEnd[t] = 0; S.subCnt[t] = 0; }
+    __syncthreads();
     const uint32_t entry = S.entry;
     const bool hasTok = entry < POS_SPECIAL && entry < clen;
-    HSRLE_DBG(0x2000000u | c);
     // ---- image + sub-chunk rows by bulk copies (a chunk no token starts in -- it lies inside a long literal -- needs neither)
     if (hasTok)
     {
@@ -681,17 +813,15 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       {
         fence_async_smem();
         const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
-        mbar_expect_tx(&S.mbar[0], bytes + (uint32_t)sizeof(S.sub));
+        mbar_expect_tx(&S.mbar[0], bytes + SUBROW_BYTES);
         bulk_load(S.img, in + c0, bytes, &S.mbar[0]);
-        bulk_load(S.sub, D.subMap + (size_t)c * DEC_NSUB * DEC_WIN, (uint32_t)sizeof(S.sub), &S.mbar[0]);
+        bulk_load(S.tile, D.subMap + (size_t)c * DEC_NSUB * DEC_WIN, SUBROW_BYTES, &S.mbar[0]);
       }
       if (!mbar_wait(&S.mbar[0], phase0)) cnt.emitBad = 0x200;
       phase0 ^= 1u;
     }
     HSRLE_DBG(0x3000000u | c);
     // ---- sub-chunk entries: hops through the sub-chunk rows (a landing outside a window is walked token by token)
-    if (t < DEC_NSUB) { S.subEntry[t] = 0xFFFFFFFFu; }
-    __syncthreads();
     if (t == 0 && hasTok)
     {
       uint32_t x = entry - c0;
@@ -700,11 +830,11 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
         const uint32_t s = x / DEC_SB, os = x - s * DEC_SB;
         if (S.subEntry[s] == 0xFFFFFFFFu) S.subEntry[s] = x;
         uint32_t code;
-        if (os < DEC_WIN) code = S.sub[s][os];
+        if (os < DEC_WIN) code = subRows[s][os];
         else
         {
-          uint32_t kind; TokF f;
-          const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
+          uint32_t len, idx;
+          const uint32_t kind = tok_walk_len<W, BA, V>(S.img, x, single, availSC - x, len, idx);
           code = kind == TK_OK ? min(x + len, 0x7FFFu) : EX_BAD;   // (ends are handled by the walkers)
         }
         if (code >= EX_FAR) break;                                  // the chain ends or leaves the chunk far
@@ -713,59 +843,148 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     }
     __syncthreads();
     HSRLE_DBG(0x4000000u | c);
-    // ---- walk A (lanes 0..15 of warp 0): tokens, output bytes and symbol state of every sub-chunk
-    Agg mine = decagg_identity<K>();
-    if (warp == 0)
+    // ---- the walkers: one lane per sub-chunk (two per warp), token starts only; LUT codecs also track where every token's
+    //      symbol comes from (table slot at the start of the sub-chunk / explicit symbol) and the sub-chunk's table transform
+    if ((lane & 15) == 0)
     {
-      uint32_t myCnt = 0;
-      bool sawEnd = false, sawBad = false;
-      if (lane < DEC_NSUB && S.subEntry[lane] != 0xFFFFFFFFu)
+      const int s = warp * 2 + (lane >> 4);
+      uint32_t x = S.subEntry[s], k = 0, endKind = 0;
+      LutXf xf; if (K) lutxf_identity(xf);
+      if (x != 0xFFFFFFFFu)
       {
-        uint32_t x = S.subEntry[lane];
-        const uint32_t subEnd = (lane + 1) * DEC_SB;
+        const uint32_t subEnd = (uint32_t)(s + 1) * DEC_SB;
         while (x < subEnd)
         {
-          if (c0 + x >= clen) { sawBad = true; break; }
-          uint32_t kind; TokF f;
-          const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
-          if (kind == TK_BAD) { sawBad = true; break; }
-          const uint32_t lit = len - f.hdr;
-          // (the terminator proper -- range field 0 -- carries neither literal nor run; a zero count after the escape: last token,
-          //  its literal is still copied)
-          uint32_t runB = tok_run_bytes<W, BA, V>(f.cnt, single);
-          uint32_t litB = lit;
-          if (kind == TK_END) { runB = 0; if (len < f.hdr) litB = 0; }
-          mine.out += (uint64_t)litB + runB; myCnt++;
-          if (K) lutxf_touch(mine.xf, K, (int)f.idx, c0 + x + f.symOff);
-          else if (f.symOff != 0xFFu) mine.symPos = c0 + x + f.symOff;
-          if (kind == TK_END) { sawEnd = true; break; }
+          if (c0 + x >= clen) { endKind = 2; break; }
+          uint32_t len, idx;
+          const uint32_t kind = tok_walk_len<W, BA, V>(S.img, x, single, availSC - x, len, idx);
+          if (kind == TK_BAD) { endKind = 2; break; }
+          S.pos[s][k] = (uint16_t)x;
+          if (K)
+          {
+            lutxf_touch(xf, K, (int)idx, 8u + x + 2u);              // explicit symbols sit right behind the two head bytes (chunk-relative + 8 here)
+            S.ref[K ? s : 0][K ? k : 0] = (uint16_t)xf.e[0];
+          }
+          k++;
+          if (kind == TK_END) { endKind = 1; break; }
           x = (len >= 0x10000u) ? 0x10000u : x + len;
         }
       }
-      mine.ntok = myCnt;
-      if (sawBad) cnt.emitBad = 1;
-      if (sawEnd) cnt.endSeen = 1;
-      // exclusive prefix over the 16 sub-chunks, chunk total in lane 31
-      Agg inc = mine;
+      S.subCnt[s] = k; S.subEnd[s] = endKind;
+      if (K) S.subXf[K ? s : 0] = xf;
+    }
+    __syncthreads();
+    // ---- token counts -> exclusive prefix; end / error flags
+    if (warp == 0)
+    {
+      uint32_t v = lane < DEC_NSUB ? S.subCnt[lane] : 0u;
+      const uint32_t e = lane < DEC_NSUB ? S.subEnd[lane] : 0u;
+      if (__any_sync(0xFFFFFFFFu, e == 2u) && lane == 0) cnt.emitBad = 1;
+      if (__any_sync(0xFFFFFFFFu, e == 1u) && lane == 0) cnt.endSeen = 1;
+      uint32_t inc = v;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += o; }
+      if (lane < DEC_NSUB) S.subCnt[lane] = inc - v;
+      if (lane == DEC_NSUB - 1) S.subCnt[DEC_NSUB] = inc;
+    }
+    __syncthreads();
+    const uint32_t ntokChunk = S.subCnt[DEC_NSUB];
+    // groups of whole sub-chunks with at most DEC_NSLOT tokens each (a sub-chunk alone never has more than DX_POSCAP)
+    auto group_end = [&](uint32_t s0) -> uint32_t
+    {
+      uint32_t s1 = s0 + 1;
+      while (s1 < (uint32_t)DEC_NSUB && S.subCnt[s1 + 1] - S.subCnt[s0] <= DEC_NSLOT) s1++;
+      return s1;
+    };
+    // parse the tokens of sub-chunks [s0, s1) in parallel (four consecutive tokens per thread), scan output bytes and the
+    // last explicit symbol; with `keep` the records are stored
+    auto parse_group = [&](uint32_t s0, uint32_t s1, bool keep, unsigned long long outBase, uint32_t symBase, unsigned long long &gOut, uint32_t &gSym)
+    {
+      const uint32_t tok0 = S.subCnt[s0], nt = S.subCnt[s1] - tok0;
+      uint32_t lit[4], run[4], src[4], sy[4], sb[4];
+      unsigned long long myOut = 0; uint32_t mySym = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
       {
-        const Agg o = decagg_shfl_up<K>(inc, d);
-        if (lane >= d) inc = decagg_combine<K>(o, inc);
+        const uint32_t i = (uint32_t)t * 4 + j;
+        lit[j] = 0; run[j] = 0; src[j] = 0; sy[j] = 0; sb[j] = 0;
+        if (i < nt)
+        {
+          uint32_t s = s0;
+          while (S.subCnt[s + 1] <= tok0 + i) s++;                 // (sub-chunks without tokens are stepped over)
+          const uint32_t k = tok0 + i - S.subCnt[s];
+          const uint32_t x = S.pos[s][k];
+          uint32_t kind; TokF f;
+          const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
+          uint32_t runB = tok_run_bytes<W, BA, V>(f.cnt, single), litB = len - f.hdr;
+          if (kind == TK_END) { runB = 0; if (len < f.hdr) litB = 0; }
+          lit[j] = litB; run[j] = runB; src[j] = x + f.hdr; sb[j] = s;
+          if (K) sy[j] = S.ref[K ? s : 0][K ? k : 0];
+          else sy[j] = f.symOff != 0xFFu ? x + f.symOff + 1u : 0u;   // + 1: 0 means "no explicit symbol"
+          myOut += (unsigned long long)litB + runB;
+          if (!K) mySym = max(mySym, sy[j]);
+        }
       }
-      Agg ex = decagg_shfl_up<K>(inc, 1);
-      if (lane == 0) ex = decagg_identity<K>();
-      if (lane < DEC_NSUB) { S.subCnt[lane] = ex.ntok; S.subOut[lane] = ex.out; }
-      if (lane == 31) { S.subCnt[DEC_NSUB] = inc.ntok; S.subOut[DEC_NSUB] = inc.out; }
-      Agg tot = inc;                                                  // the chunk's total: lane 31's inclusive value
-      tot.out = __shfl_sync(0xFFFFFFFFu, inc.out, 31); tot.ntok = __shfl_sync(0xFFFFFFFFu, inc.ntok, 31); tot.symPos = __shfl_sync(0xFFFFFFFFu, inc.symPos, 31);
+      unsigned long long exOut; uint32_t exSym;
+      block_scan(myOut, mySym, exOut, exSym, gOut, gSym);
+      if (keep)
+      {
+        unsigned long long o = outBase + exOut; uint32_t ls = max(symBase, exSym);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+          const uint32_t i = (uint32_t)t * 4 + j;
+          if (i < nt)
+          {
+            if (!K) ls = max(ls, sy[j]);
+            S.rOut[i] = (uint32_t)min(o, (unsigned long long)0xFFFFFFFFu); S.rLit[i] = lit[j]; S.rRun[i] = run[j]; S.rSrc[i] = (uint16_t)src[j];
+            S.rSymI[i] = K ? (uint16_t)sy[j] : (uint16_t)(ls ? ls - 1u : 0xFFFFu); S.rSub[i] = (uint8_t)sb[j];
+            o += (unsigned long long)lit[j] + run[j];
+          }
+        }
+        if (t == 0) S.rOut[nt] = (uint32_t)min(outBase + gOut, (unsigned long long)0xFFFFFFFFu);      // sentinel: where the group ends
+      }
+    };
+    // ---- chunk totals (single group: its records are kept)
+    const uint32_t gEnd0 = group_end(0);
+    const bool oneGroup = gEnd0 == (uint32_t)DEC_NSUB;
+    unsigned long long chunkOutLen = 0; uint32_t chunkSym = 0;
+    for (uint32_t s0 = 0; s0 < (uint32_t)DEC_NSUB;)
+    {
+      const uint32_t s1 = group_end(s0);
+      unsigned long long gOut; uint32_t gSym;
+      parse_group(s0, s1, oneGroup, 0ull, 0u, gOut, gSym);
+      chunkOutLen += gOut; chunkSym = max(chunkSym, gSym);
+      s0 = s1;
+    }
+    HSRLE_DBG(0x5000000u | c);
+    // ---- publish the chunk's aggregate, look back for the exclusive prefix (decoupled look-back, 32 chunks per step), symbol state
+    if (warp == 0)
+    {
+      Agg tot = decagg_identity<K>();
+      tot.out = chunkOutLen; tot.ntok = ntokChunk; tot.symPos = chunkSym ? c0 + chunkSym - 1u : 0u;
+      Agg ex = decagg_identity<K>();                                   // K > 0: table transform of the sub-chunks before mine
       if (K)
       {
+        Agg mine = decagg_identity<K>();
+        if (lane < DEC_NSUB)
+        { // the walkers' entries are chunk-relative + 8: make them stream positions
+          mine.xf = S.subXf[K ? lane : 0];
+#pragma unroll
+          for (int i = 0; i < 7; i++) if (i < K && mine.xf.e[i] >= 8u) mine.xf.e[i] += c0 - 8u;
+        }
+        Agg inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const Agg o = decagg_shfl_up<K>(inc, d);
+          if (lane >= d) inc = decagg_combine<K>(o, inc);
+        }
+        ex = decagg_shfl_up<K>(inc, 1);
+        if (lane == 0) ex = decagg_identity<K>();
 #pragma unroll
         for (int i = 0; i < 7; i++) if (i < K) tot.xf.e[i] = __shfl_sync(0xFFFFFFFFu, inc.xf.e[i], 31);
       }
-      HSRLE_DBG(0x5000000u | c);
-      // ---- publish the chunk's aggregate, look back for the exclusive prefix (decoupled look-back, 32 chunks per step)
       if (lane == 0) { decagg_store<K>(&aggBuf[c], tot); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
       Agg excl = decagg_identity<K>();
       int64_t base = (int64_t)c - 1;
@@ -809,78 +1028,47 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
         decagg_store<K>(&incBuf[c], incl); __threadfence(); st_volatile_u32(D.flagAgg + c, 2u);
         if (c == nChunks - 1) { cnt.outTotal = incl.out; cnt.nTok = incl.ntok; }
         decagg_store<K>(&S.bc, excl);
+        if (!K) S.inSym = single ? (uint64_t)hs.singleSym : (excl.symPos ? load_sym(in + excl.symPos, W) : 0ull);
       }
-      // ---- symbol state at the start of every sub-chunk
-      {
-        const Agg before = decagg_combine<K>(excl, ex);              // everything before my sub-chunk
-        if (lane < DEC_NSUB)
-        {
-          if (K)
-          {
-            Lut l0; lut_init(l0, W);
-            Lut l1; lutxf_apply(before.xf, K, W, in, l0, l1);
-            S.subLut[K ? lane : 0] = l1;
-          }
-          else S.subSym[lane] = single ? (uint64_t)hs.singleSym : (before.symPos ? load_sym(in + before.symPos, W) : 0ull);
-        }
+      if (K && lane < DEC_NSUB)
+      { // the table at the start of every sub-chunk
+        const Agg before = decagg_combine<K>(excl, ex);
+        Lut l0; lut_init(l0, W);
+        Lut l1; lutxf_apply(before.xf, K, W, in, l0, l1);
+        S.subLut[K ? lane : 0] = l1;
       }
     }
     __syncthreads();
     HSRLE_DBG(0x6000000u | c);
-    const uint32_t ntokChunk = S.subCnt[DEC_NSUB];
-    const uint64_t chunkOut0 = S.bc.out, chunkOutLen = S.subOut[DEC_NSUB];
-    // ---- expansion in passes of DEC_NSLOT tokens
-    for (uint32_t pass0 = 0; pass0 < ntokChunk; pass0 += DEC_NSLOT)
+    const uint64_t chunkOut0 = S.bc.out;
+    // run symbol of a token record
+    auto rec_sym = [&](uint32_t r) -> uint64_t
     {
-      const uint32_t passN = min(DEC_NSLOT, ntokChunk - pass0);
+      const uint32_t v = S.rSymI[r];
+      if (K) return v < 8u ? lut_get(S.subLut[K ? S.rSub[r] : 0], K, (int)v) : img_sym<W>(S.img, v - 8u);
+      return v == 0xFFFFu ? S.inSym : img_sym<W>(S.img, v);
+    };
+    // ---- expansion, group by group
+    unsigned long long outBase = 0; uint32_t symBase = 0;
+    for (uint32_t s0 = 0; s0 < (uint32_t)DEC_NSUB && ntokChunk;)
+    {
+      const uint32_t s1 = group_end(s0);
+      const uint32_t passN = S.subCnt[s1] - S.subCnt[s0];
       __syncthreads();
-      if (t == 0) { S.nSkip = 0; }
-      // -- walk B: token records of the pass
-      if (warp == 0 && lane < DEC_NSUB && S.subEntry[lane] != 0xFFFFFFFFu)
+      if (!oneGroup)
       {
-        const uint32_t k0 = S.subCnt[lane], k1 = (lane + 1 < DEC_NSUB) ? S.subCnt[lane + 1] : ntokChunk;
-        if (k1 > pass0 && k0 < pass0 + passN)
-        {
-          uint32_t x = S.subEntry[lane], k = k0;
-          uint64_t o = S.subOut[lane];
-          uint64_t symReg = K ? 0ull : S.subSym[lane];
-          Lut lut; if (K) lut = S.subLut[K ? lane : 0]; else lut_init(lut, W);
-          while (k < k1 && k < pass0 + passN)
-          {
-            uint32_t kind; TokF f;
-            const uint32_t len = toklen_at<W, BA, V>(S.img, x, single, availSC - x, kind, f);
-            uint32_t runB = tok_run_bytes<W, BA, V>(f.cnt, single);
-            uint32_t litB = len - f.hdr;
-            if (kind == TK_END) { runB = 0; if (len < f.hdr) litB = 0; }
-            uint64_t sym;
-            if (K)
-            {
-              if (f.idx == (uint32_t)K) { uint64_t sv = 0; for (int i = 0; i < W; i++) sv |= (uint64_t)S.img[x + f.symOff + i] << (8 * i); lut_touch(lut, K, K, sv); }
-              else if (f.idx > 0) { const uint64_t sv = lut_get(lut, K, (int)f.idx); lut_touch(lut, K, (int)f.idx, sv); }
-              sym = lut.s[0];
-            }
-            else
-            {
-              if (f.symOff != 0xFFu) { uint64_t sv = 0; for (int i = 0; i < W; i++) sv |= (uint64_t)S.img[x + f.symOff + i] << (8 * i); symReg = sv; }
-              sym = symReg;
-            }
-            if (k >= pass0)
-            {
-              const uint32_t r = k - pass0;
-              S.rOut[r] = (uint32_t)min(o, (uint64_t)0xFFFFFFFFu); S.rLit[r] = litB; S.rRun[r] = runB; S.rSrc[r] = x + f.hdr; S.rSym[r] = sym;
-            }
-            o += (uint64_t)litB + runB; k++;
-            if (kind != TK_OK) break;
-            x += len;
-          }
-          if (k == pass0 + passN) S.rOut[passN] = (uint32_t)min(o, (uint64_t)0xFFFFFFFFu);     // sentinel: where the pass ends
-        }
+        unsigned long long gOut; uint32_t gSym;
+        parse_group(s0, s1, true, outBase, symBase, gOut, gSym);
+        outBase += gOut; symBase = max(symBase, gSym);
       }
+      s0 = s1;
+      if (t == 0) { S.nSkip = 0; }
       __syncthreads();
+      if (passN == 0) continue;
       HSRLE_DBG(0x7000000u | c);
-      // output range of the pass, absolute (never beyond the declared size)
+      // output range of the group, absolute (never beyond the declared size)
       const uint64_t pLo = min(chunkOut0 + S.rOut[0], (uint64_t)n);
-      const uint64_t pHi = min(chunkOut0 + ((pass0 + passN >= ntokChunk) ? chunkOutLen : (uint64_t)S.rOut[passN]), (uint64_t)n);
+      const uint64_t pHi = min(chunkOut0 + S.rOut[passN], (uint64_t)n);
       if (pHi <= pLo) continue;
       const uint64_t T0 = pLo & ~(uint64_t)15;
       const uint32_t nTiles = (uint32_t)((pHi - T0 + DEC_TILE - 1) / DEC_TILE);
@@ -904,7 +1092,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
             if (idx >= D.bigCap) { S.skipLo[slot] = 0; S.skipHi[slot] = 0; continue; }
             S.skipLo[slot] = (uint32_t)kA; S.skipHi[slot] = (uint32_t)kB;
             DecBigOp &op = D.bigList[idx];
-            op.dst = (uint32_t)(T0 + kA * DEC_TILE); op.len = (uint32_t)((kB - kA) * DEC_TILE); op.kind = (uint32_t)part; op.sym = S.rSym[r];
+            op.dst = (uint32_t)(T0 + kA * DEC_TILE); op.len = (uint32_t)((kB - kA) * DEC_TILE); op.kind = (uint32_t)part; op.sym = part ? rec_sym(r) : 0ull;
             op.src = part ? (uint32_t)m : (uint32_t)(c0 + S.rSrc[r] + (T0 + kA * DEC_TILE - a));
             op.next = 0;
             __threadfence();
@@ -921,13 +1109,12 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
           for (uint32_t i = 0; i < nSkip; i++) if (tk >= S.skipLo[i] && tk < S.skipHi[i]) jump = S.skipHi[i];
           if (jump) { tk = jump - 1; continue; }
         }
-        HSRLE_DBG(0x8000000u | (tk & 0xFFFFFFu));
         const uint64_t tb = T0 + (uint64_t)tk * DEC_TILE;
         const uint64_t lo = max(tb, pLo), hi = min(tb + DEC_TILE, pHi);
         __syncthreads();                                            // the previous tile is flushed
         if (t == 0) S.nLong = 0;
         __syncthreads();
-        // -- every token of the pass that overlaps the tile: short parts by the token's thread, long parts listed
+        // -- every token of the group that overlaps the tile: short parts by the token's thread, long parts listed
         for (uint32_t r = t; r < passN; r += DX_T)
         {
           const uint64_t a = chunkOut0 + S.rOut[r];
@@ -939,7 +1126,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
             if (pb > pa)
             {
               const uint32_t len = (uint32_t)(pb - pa), d = (uint32_t)(pa - tb), rel = S.rSrc[r] + (uint32_t)(pa - a);
-              if (len <= DX_INLINE) { for (uint32_t i = 0; i < len; i++) S.tile[d + i] = (uint8_t)lit_byte(S.img, in, c0, rel + i); }
+              if (len <= DX_INLINE) thread_copy(S.tile, d, len, S.img, in, c0, rel);
               else { const uint32_t q = atomicAdd(&S.nLong, 1u); if (q < DX_LONGCAP) S.longList[q] = r * 2u; }
             }
           }
@@ -948,12 +1135,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
             if (pb > pa)
             {
               const uint32_t len = (uint32_t)(pb - pa), d = (uint32_t)(pa - tb);
-              if (len <= DX_INLINE)
-              {
-                const uint64_t sym = S.rSym[r];
-                uint32_t ph = (uint32_t)((pa - m) % (uint32_t)W);
-                for (uint32_t i = 0; i < len; i++) { S.tile[d + i] = (uint8_t)run_byte<W>(sym, ph); ph = (ph + 1 == (uint32_t)W) ? 0u : ph + 1; }
-              }
+              if (len <= DX_INLINE) thread_fill<W>(S.tile, d, len, rec_sym(r), (uint32_t)((pa - m) % (uint32_t)W));
               else { const uint32_t q = atomicAdd(&S.nLong, 1u); if (q < DX_LONGCAP) S.longList[q] = r * 2u + 1u; }
             }
           }
@@ -975,7 +1157,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
             else
             {
               const uint64_t pa = max(m, lo), pb = min(e, hi);
-              warp_fill<W>(S.tile, (uint32_t)(pa - tb), (uint32_t)(pb - pa), S.rSym[r], (uint32_t)((pa - m) % (uint32_t)W), lane);
+              warp_fill<W>(S.tile, (uint32_t)(pa - tb), (uint32_t)(pb - pa), rec_sym(r), (uint32_t)((pa - m) % (uint32_t)W), lane);
             }
           }
         }
@@ -1014,17 +1196,24 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     }
   }
 
-  // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken
-  for (uint32_t guard = 0;; guard++)
+  // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken.  One thread
+  //      polls (the others wait at the barrier and cost no issue slots).
+  uint32_t seenBig = 0;
+  for (uint32_t guard = 0; guard < (1u << 24); guard++)
   {
-    if (guard > (1u << 22)) { if (t == 0) cnt.emitBad = 0x500; break; }
-    HSRLE_DBG(0xA000000u | (guard & 0xFFFFFFu));
     __syncthreads();
     if (t == 0)
-    { // (one reader: the loop below must run the same number of times in every thread; "all done" is sampled first)
-      S.flag = (ld_volatile_u32(&cnt.chunksDone) >= nChunks) ? 1u : 0u;
-      __threadfence();
-      S.entry = min(ld_volatile_u32(&cnt.nBig), D.bigCap);
+    { // "all done" is sampled before the operation count: whatever was registered before the last chunk finished is seen
+      uint32_t done, nb, spin = 0;
+      for (;;)
+      {
+        done = (ld_volatile_u32(&cnt.chunksDone) >= nChunks) ? 1u : 0u;
+        __threadfence();
+        nb = min(ld_volatile_u32(&cnt.nBig), D.bigCap);
+        if (done || nb > seenBig || ++spin > (1u << 22)) break;
+        __nanosleep(1000);
+      }
+      S.flag = done; S.entry = nb;
     }
     __syncthreads();
     const bool allDone = S.flag != 0;
@@ -1045,16 +1234,15 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       for (;;)
       {
         __syncthreads();
-        if (t == 0) S.bcast = atomicAdd(&op.next, 1u);
+        if (t == 0) S.bcast = (ld_volatile_u32(&op.next) >= np) ? np : atomicAdd(&op.next, 1u);
         __syncthreads();
         const uint32_t k = S.bcast;
         if (k >= np) break;
-        HSRLE_DBG(0xB000000u | (i << 16) | (k & 0xFFFFu));
         dec_big_piece<W, K>(D, S, o, k * DEC_BIG_PIECE, min(DEC_BIG_PIECE, o.len - k * DEC_BIG_PIECE), phase0, phase1);
       }
     }
+    if (!pending) seenBig = nb;
     if (allDone && !pending) break;
-    if (!allDone) __nanosleep(500);
   }
 }
 
