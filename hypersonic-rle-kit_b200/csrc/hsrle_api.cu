@@ -379,7 +379,9 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
       fflush(stderr);
       _exit(3);
     }
-    fprintf(stderr, "[hsrle] k_dec_emit done: %s (grid %u)\n", cudaGetErrorString(cudaStreamSynchronize(st)), D.emitGrid); fflush(stderr);
+    fprintf(stderr, "[hsrle] k_dec_emit done: %s (grid %u); phase ticks/64:", cudaGetErrorString(cudaStreamSynchronize(st)), D.emitGrid);
+    for (int i = 0; i < 12; i++) fprintf(stderr, " %u", hDbg[3000 + i]);
+    fprintf(stderr, "\n"); fflush(stderr);
   }
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }

@@ -11,6 +11,17 @@ namespace hsrle {
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) { return ld_volatile_u32g(p); }
 __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) { st_volatile_u32g(p, v); }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---- 1-D bulk copies (TMA) global -> shared, completion on an mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
@@ -421,11 +432,27 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
       }
     }
     __syncthreads();
-    // ---- chunk level, in place, for EVERY offset: 512-byte blocks in reverse order (a code below the end of the chunk points into a
-    //      later block, final already) -- one look-up per offset
-    for (int b = (int)(DEC_CB / 512) - 2; b >= 0; b--)
+    // ---- chunk level, in place, for EVERY offset.  First every warp finishes its own 2-KiB region (512-byte blocks in reverse order:
+    //      a code below the end of the region points into a later block of it, final already; warp barriers only), then the regions
+    //      in reverse order by the whole CTA (a code below the end of the chunk points into a later region) -- one look-up per offset
     {
-      for (uint32_t p = (uint32_t)b * 512 + t; p < (uint32_t)(b + 1) * 512; p += DM_T)
+      const uint32_t r0 = (uint32_t)(t >> 5) * 2048u, r1 = r0 + 2048u;
+      for (int b = 2; b >= 0; b--)
+      {
+#pragma unroll 4
+        for (uint32_t p = r0 + (uint32_t)b * 512 + (t & 31); p < r0 + (uint32_t)(b + 1) * 512; p += 32)
+        {
+          const uint32_t code = ex[skew16h(p)];
+          if (code < r1) ex[skew16h(p)] = ex[skew16h(code)];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int rg = (int)(DEC_CB / 2048) - 2; rg >= 0; rg--)
+    {
+#pragma unroll 4
+      for (uint32_t p = (uint32_t)rg * 2048 + t; p < (uint32_t)(rg + 1) * 2048; p += DM_T)
       {
         const uint32_t code = ex[skew16h(p)];
         if (code < DEC_CB) ex[skew16h(p)] = ex[skew16h(code)];
@@ -510,6 +537,8 @@ template <int K> struct DecEmitSmem
   LutXf subXf[K ? DEC_NSUB : 1];                      // K > 0: table transform of every sub-chunk
   Lut subLut[K ? DEC_NSUB : 1];                       // K > 0: table at the start of the sub-chunk
   DecAgg<K> bc;                                       // look-back result
+  DecAgg<K> lbAgg[DX_T / 32];                         // look-back: per-warp combination of the window, down to its nearest inclusive prefix
+  uint32_t lbHit[DX_T / 32];
   unsigned long long warpSum[DX_T / 32 + 1];          // block scans: output bytes ...
   uint32_t warpSymI[DX_T / 32 + 1];                   // ... and last explicit symbol
   unsigned long long sumOut;                          // output bytes of the chunk / of the groups before the current one
@@ -767,7 +796,15 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   if (t == 0) { mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1); }
   uint32_t phase0 = 0, phase1 = 0;
   __syncthreads();
+#if defined(HSRLE_STAGE_MARKS)   // (hang diagnosis: build with -DHSRLE_STAGE_MARKS; every mark is a system-scope fence)
 #define HSRLE_DBG(code) do { if (D.dbg && t == 0) { *((volatile uint32_t *)D.dbg + blockIdx.x) = (uint32_t)(code); __threadfence_system(); } } while (0)
+#else
+#define HSRLE_DBG(code) do { } while (0)
+#endif
+  // phase timers (HSRLE_DEBUG): thread 0 sums the clock ticks between phase marks; dbg[3000 + phase] gets the totals (in 64-tick units)
+  unsigned long long tPh[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  long long tLast = D.dbg ? clock64() : 0;
+#define HSRLE_PH(ph) do { if (D.dbg && t == 0) { const long long now_ = clock64(); tPh[ph] += (unsigned long long)(now_ - tLast); tLast = now_; } } while (0)
 
   // block-wide exclusive scan of (output bytes, last explicit symbol) over the threads; totals returned in (totOut, totSym)
   auto block_scan = [&](unsigned long long myOut, uint32_t mySym, unsigned long long &exOut, uint32_t &exSym, unsigned long long &totOut, uint32_t &totSym)
@@ -800,6 +837,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     const uint32_t c0 = c * DEC_CB;
     const uint32_t availSC = clen - c0;
     HSRLE_DBG(0x1000000u | c);
+    HSRLE_PH(0);
     // ---- the chunk's first true token start (K1's resolver)
     if (t == 0) S.entry = __ldcg(D.chunkEntry + c);
     if (t < DEC_NSUB) { S.subEntry[t] = 0xFFFFFFFFu; S.subEnd[t] = 0; S.subCnt[t] = 0; }
@@ -821,6 +859,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       phase0 ^= 1u;
     }
     HSRLE_DBG(0x3000000u | c);
+    HSRLE_PH(1);
     // ---- sub-chunk entries: hops through the sub-chunk rows (a landing outside a window is walked token by token)
     if (t == 0 && hasTok)
     {
@@ -843,6 +882,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     }
     __syncthreads();
     HSRLE_DBG(0x4000000u | c);
+    HSRLE_PH(2);
     // ---- the walkers: one lane per sub-chunk (two per warp), token starts only; LUT codecs also track where every token's
     //      symbol comes from (table slot at the start of the sub-chunk / explicit symbol) and the sub-chunk's table transform
     if ((lane & 15) == 0)
@@ -874,6 +914,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       if (K) S.subXf[K ? s : 0] = xf;
     }
     __syncthreads();
+    HSRLE_PH(3);
     // ---- token counts -> exclusive prefix; end / error flags
     if (warp == 0)
     {
@@ -958,12 +999,14 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       s0 = s1;
     }
     HSRLE_DBG(0x5000000u | c);
-    // ---- publish the chunk's aggregate, look back for the exclusive prefix (decoupled look-back, 32 chunks per step), symbol state
+    HSRLE_PH(4);
+    // ---- publish the chunk's aggregate; decoupled look-back for the exclusive prefix, 256 chunks per step (one per thread; the first
+    //      wave of CTAs starts together, so the look-back is deep there); symbol state
+    Agg tot = decagg_identity<K>();
+    Agg subEx = decagg_identity<K>();                                 // K > 0 (warp 0): table transform of the sub-chunks before lane's
     if (warp == 0)
     {
-      Agg tot = decagg_identity<K>();
       tot.out = chunkOutLen; tot.ntok = ntokChunk; tot.symPos = chunkSym ? c0 + chunkSym - 1u : 0u;
-      Agg ex = decagg_identity<K>();                                   // K > 0: table transform of the sub-chunks before mine
       if (K)
       {
         Agg mine = decagg_identity<K>();
@@ -980,59 +1023,69 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
           const Agg o = decagg_shfl_up<K>(inc, d);
           if (lane >= d) inc = decagg_combine<K>(o, inc);
         }
-        ex = decagg_shfl_up<K>(inc, 1);
-        if (lane == 0) ex = decagg_identity<K>();
+        subEx = decagg_shfl_up<K>(inc, 1);
+        if (lane == 0) subEx = decagg_identity<K>();
 #pragma unroll
         for (int i = 0; i < 7; i++) if (i < K) tot.xf.e[i] = __shfl_sync(0xFFFFFFFFu, inc.xf.e[i], 31);
       }
-      if (lane == 0) { decagg_store<K>(&aggBuf[c], tot); __threadfence(); st_volatile_u32(D.flagAgg + c, 1u); }
-      Agg excl = decagg_identity<K>();
-      int64_t base = (int64_t)c - 1;
-      while (base >= 0)
+      if (lane == 0) { decagg_store<K>(&aggBuf[c], tot); st_release_u32(D.flagAgg + c, 1u); }
+    }
+    Agg excl = decagg_identity<K>();                                  // (maintained by warp 0)
+    for (int64_t base = (int64_t)c - 1; base >= 0; base -= DX_T)
+    {
+      const int64_t p = base - t;
+      uint32_t fl = 2u;                                               // threads before chunk 0 behave like an (identity) inclusive prefix
+      Agg v = decagg_identity<K>();
+      if (p >= 0)
       {
-        const int64_t p = base - lane;
-        uint32_t fl = 2u;                                           // lanes before chunk 0 behave like an (identity) inclusive prefix
-        Agg v = decagg_identity<K>();
-        if (p >= 0)
-        {
-          uint32_t spin = 0;
-          do { fl = ld_volatile_u32(D.flagAgg + p); } while (fl == 0u && ++spin < (1u << 24));
-          if (fl == 0u) { cnt.emitBad = 0x400; fl = 2u; }            // (cannot happen: chunks are taken in order)
-          __threadfence();
-          v = decagg_load_cg<K>(fl == 2u ? &incBuf[p] : &aggBuf[p]);
-        }
-        const uint32_t incMask = __ballot_sync(0xFFFFFFFFu, fl == 2u);
-        const int j = incMask ? (__ffs(incMask) - 1) : 32;           // nearest inclusive prefix in this window
-        if (lane > j) v = decagg_identity<K>();
-        // ordered reduction: lane l ends with the combination of lanes l .. 31 (older lanes are the higher ones)
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-          const Agg o = decagg_shfl_down<K>(v, d);
-          if (lane + d < 32) v = decagg_combine<K>(o, v);
-        }
-        Agg w0 = v;
-        w0.out = __shfl_sync(0xFFFFFFFFu, v.out, 0); w0.ntok = __shfl_sync(0xFFFFFFFFu, v.ntok, 0); w0.symPos = __shfl_sync(0xFFFFFFFFu, v.symPos, 0);
-        if (K)
-        {
-#pragma unroll
-          for (int i = 0; i < 7; i++) if (i < K) w0.xf.e[i] = __shfl_sync(0xFFFFFFFFu, v.xf.e[i], 0);
-        }
-        excl = decagg_combine<K>(w0, excl);
-        if (incMask) break;
-        base -= 32;
+        uint32_t spin = 0;
+        do { fl = ld_acquire_u32(D.flagAgg + p); } while (fl == 0u && ++spin < (1u << 24));
+        if (fl == 0u) { cnt.emitBad = 0x400; fl = 2u; }              // (cannot happen: chunks are taken in order)
+        v = decagg_load_cg<K>(fl == 2u ? &incBuf[p] : &aggBuf[p]);
       }
+      const uint32_t incMask = __ballot_sync(0xFFFFFFFFu, fl == 2u);
+      const int j = incMask ? (__ffs(incMask) - 1) : 32;             // nearest inclusive prefix in this warp's window
+      if (lane > j) v = decagg_identity<K>();
+      // ordered reduction: lane 0 ends with the combination of lanes 0 .. 31 (older chunks are the higher lanes)
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const Agg o = decagg_shfl_down<K>(v, d);
+        if (lane + d < 32) v = decagg_combine<K>(o, v);
+      }
+      if (lane == 0) { decagg_store<K>(&S.lbAgg[warp], v); S.lbAgg[warp].ntok = v.ntok; S.lbHit[warp] = incMask ? 1u : 0u; }
+      __syncthreads();
+      if (warp == 0)
+      { // merge the warps' windows, nearest first, until one reached an inclusive prefix
+        bool hit = false;
+        Agg r = decagg_identity<K>();
+        for (int w = 0; w < DX_T / 32 && !hit; w++)
+        {
+          Agg a = decagg_identity<K>();
+          a.out = S.lbAgg[w].out; a.ntok = S.lbAgg[w].ntok; a.symPos = S.lbAgg[w].symPos;
+          if (K) a.xf = S.lbAgg[w].xf;
+          r = decagg_combine<K>(a, r);
+          hit = S.lbHit[w] != 0;
+        }
+        excl = decagg_combine<K>(r, excl);
+        if (lane == 0) S.flag = hit ? 1u : 0u;
+      }
+      __syncthreads();
+      if (S.flag) break;
+    }
+    if (warp == 0)
+    {
       const Agg incl = decagg_combine<K>(excl, tot);
       if (lane == 0)
       {
-        decagg_store<K>(&incBuf[c], incl); __threadfence(); st_volatile_u32(D.flagAgg + c, 2u);
+        decagg_store<K>(&incBuf[c], incl); st_release_u32(D.flagAgg + c, 2u);
         if (c == nChunks - 1) { cnt.outTotal = incl.out; cnt.nTok = incl.ntok; }
         decagg_store<K>(&S.bc, excl);
         if (!K) S.inSym = single ? (uint64_t)hs.singleSym : (excl.symPos ? load_sym(in + excl.symPos, W) : 0ull);
       }
       if (K && lane < DEC_NSUB)
       { // the table at the start of every sub-chunk
-        const Agg before = decagg_combine<K>(excl, ex);
+        const Agg before = decagg_combine<K>(excl, subEx);
         Lut l0; lut_init(l0, W);
         Lut l1; lutxf_apply(before.xf, K, W, in, l0, l1);
         S.subLut[K ? lane : 0] = l1;
@@ -1040,6 +1093,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     }
     __syncthreads();
     HSRLE_DBG(0x6000000u | c);
+    HSRLE_PH(5);
     const uint64_t chunkOut0 = S.bc.out;
     // run symbol of a token record
     auto rec_sym = [&](uint32_t r) -> uint64_t
@@ -1114,6 +1168,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
         __syncthreads();                                            // the previous tile is flushed
         if (t == 0) S.nLong = 0;
         __syncthreads();
+        HSRLE_PH(6);
         // -- every token of the group that overlaps the tile: short parts by the token's thread, long parts listed
         for (uint32_t r = t; r < passN; r += DX_T)
         {
@@ -1141,6 +1196,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
           }
         }
         __syncthreads();
+        HSRLE_PH(7);
         // -- long parts: one warp each
         {
           const uint32_t nl = min(S.nLong, (uint32_t)DX_LONGCAP);
@@ -1162,6 +1218,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
           }
         }
         __syncthreads();
+        HSRLE_PH(8);
         // -- flush: whole vectors with 16-byte stores, the ragged ends (shared with the neighbouring chunks) byte-wise
         {
           const uint32_t b0 = (uint32_t)(lo - tb), b1 = (uint32_t)(hi - tb);
@@ -1178,6 +1235,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       }
     }
     HSRLE_DBG(0x9000000u | c);
+    HSRLE_PH(9);
     // ---- chunk done; the last one settles the status and the result
     __syncthreads();
     if (t == 0)
@@ -1196,6 +1254,8 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     }
   }
 
+  HSRLE_PH(10);
+  if (D.dbg && t == 0) { for (int i = 0; i < 12; i++) atomicAdd(D.dbg + 3000 + i, (uint32_t)(tPh[i] >> 6)); }
   // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken.  One thread
   //      polls (the others wait at the barrier and cost no issue slots).
   uint32_t seenBig = 0;

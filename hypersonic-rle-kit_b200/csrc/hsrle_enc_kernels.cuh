@@ -370,7 +370,10 @@ template <int W, int BA, int V, class SymT> struct EncCta
     total = shfl_idx_t(inc, 31);
   }
 
-  static __device__ void process(const EncBufs &B, WarpRecs &R, uint32_t s, bool given, const AutoState &gSt, const LutR &gLut, Seg &totalOut)
+  //      reuse: the super-chunk was evaluated before -- every lane starts from the state it converged to last time (B.cIn / B.cLut,
+  //      the table rebuilt under the new incoming one) instead of a warmed-up guess: a re-run after a changed incoming table then
+  //      settles in one or two scans instead of half a dozen.
+  static __device__ void process(const EncBufs &B, WarpRecs &R, uint32_t s, bool given, const AutoState &gSt, const LutR &gLut, Seg &totalOut, bool reuse = false)
   {
     constexpr Spec sp = make_spec(W, BA, V);
     const int lane = threadIdx.x & 31;
@@ -395,6 +398,18 @@ template <int W, int BA, int V, class SymT> struct EncCta
     AutoState stIn; LutR lutIn;
     if (lane == 0 && given) { stIn = gSt; lutIn = gLut; }
     else if (lane == 0 && s == 0) enc_stream_incoming(B, W, stIn, lutIn);
+    else if (given && reuse && active)
+    {
+      const uint32_t chunk = s * E2_T + (uint32_t)lane * (E2L_CH / E2_CH);
+      stIn = B.cIn[chunk];
+      if constexpr (K != 0)
+      {
+        Lut g = B.cLut[chunk], gi; lut_to(gi, gLut);
+        enc_chunk_lut(g, B.cKnown[chunk], K, gi);
+        lut_from(lutIn, g);
+      }
+      else lut_init(lutIn, W);
+    }
     else
     { // warm up over the preceding E2_WARM records from the neutral guess
       const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
@@ -696,7 +711,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
       __syncthreads();
       if (need)
       {
-        if (warp == 0) { process(B, S.r[0], s, true, run, runLut, tot); if (lane == 0) S.bcTot = tot; }
+        if (warp == 0) { process(B, S.r[0], s, true, run, runLut, tot, true); if (lane == 0) S.bcTot = tot; }
         __syncthreads();
         tot = S.bcTot;
         if (t == 0) { B.scIn[s] = run; if (K) lut_to(B.scLut[s], runLut); B.scDirty[s] = 0; atomicAdd(&sc.serialSC, 1u); }
@@ -776,7 +791,7 @@ __device__ __forceinline__ void enc_fix_tickets(const EncBufs &B, typename EncCt
         else lut_init(gl, W);
       }
       typename C::Seg tot;
-      C::process(B, R, s, true, g, gl, tot);
+      C::process(B, R, s, true, g, gl, tot, true);
     }
     __syncwarp();
     if (lane == 0) { __threadfence(); atomicAdd(&sc.fixDone, 1u); }
@@ -857,7 +872,7 @@ __global__ void __launch_bounds__(FIX_T, 1) k_enc_fix(const EncBufs B, int start
         if (!listed && !B.scDirty[s]) continue;
         AutoState g = B.scIn[s]; typename C::LutR gl; if (C::K) lut_from(gl, B.scLut[s]); else lut_init(gl, W);
         typename C::Seg tot;
-        C::process(B, S.r[warp], s, true, g, gl, tot);
+        C::process(B, S.r[warp], s, true, g, gl, tot, true);
       }
       __threadfence_block();
       __syncthreads();
