@@ -123,6 +123,12 @@ static uint32_t enc_scan_steps(uint32_t nVec)
 
 // grid of the verify / repair kernel: the master CTA plus helpers for rounds with many dirty super-chunks.  Few super-chunks
 // (small inputs) never have such rounds: the master alone.
+// super-chunks a repair warp follows a changed state through per round (1: none); HSRLE_FOLLOW overrides (experiments)
+static int enc_follow_hops()
+{
+  static const int v = getenv("HSRLE_FOLLOW") ? std::max(1, atoi(getenv("HSRLE_FOLLOW"))) : 1;
+  return v;
+}
 static int enc_fix_grid(const EncBufs &B, int sms)
 {
   return B.maxSC <= 4 * FIX_SOLO ? 1 : std::min<int>(sms, 1 + (int)(B.maxSC / 64));
@@ -242,7 +248,7 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
   const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
   HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B);
-  HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K));
+  HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K), enc_follow_hops());
   HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);
   HSRLE_LAUNCH(k_enc_copy_big, sms * 4, 256, 0, st, B);
   return cuda_ok(cudaGetLastError(), "encode launch") ? 0 : 2;
@@ -303,11 +309,11 @@ static int slice_phase(const hsrle_slice_job *J, int phase, cudaStream_t st)
     case 1:   // boundary-run fix-up, automaton from the assumed incoming state
       HSRLE_LAUNCH(k_enc_slice_link, 1, 32, 0, st, B, sp);
       HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B);
-      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K));
+      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K), enc_follow_hops());
       break;
     case 2:   // true incoming state, repair rounds
       HSRLE_LAUNCH(k_enc_slice_inject, 1, 32, 0, st, B, sp);
-      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, 1, FIX_T, k->fixSmem, st, B, 1, enc_rounds(sp.W, sp.K));
+      HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, 1, FIX_T, k->fixSmem, st, B, 1, enc_rounds(sp.W, sp.K), enc_follow_hops());
       break;
     case 3:   // tokens
       HSRLE_LAUNCH_NAMED("k_enc_emit", k->emit, autoGrid, E2_T, k->emitSmem, st, B);

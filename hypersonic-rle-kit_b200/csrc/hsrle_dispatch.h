@@ -11,7 +11,7 @@ struct EncKernels
 {
   void (*scan)(const EncBufs);
   void (*autom)(const EncBufs);
-  void (*fix)(const EncBufs, int, int);
+  void (*fix)(const EncBufs, int, int, int);
   void (*emit)(const EncBufs);
   size_t autoSmem, fixSmem, emitSmem;
   int symBytes;           // 4 or 8: element size of EncBufs::runSym

@@ -278,6 +278,7 @@ template <int W, int BA, int V, class SymT> struct EncCta
   {
     WarpRecs r[FIX_W];
     Seg warpTot[FIX_W];
+    Seg scanTot;
     Seg bcTot;
     AutoState bcSt; LutR bcLut;                                 // broadcast slots
     uint64_t warpBytes[FIX_W];
@@ -330,15 +331,24 @@ template <int W, int BA, int V, class SymT> struct EncCta
     Seg ex = shfl_up_t(inc, 1);
     if (lane == 0) ex = segsum_identity<K, AggR>();
     __syncthreads();
-    Seg pre = segsum_identity<K, AggR>();
-    total = segsum_identity<K, AggR>();
-#pragma unroll 1
-    for (int w = 0; w < FIX_W; w++)
-    {
-      const Seg t = S.warpTot[w];
-      if (w < warp) pre = segsum_combine(pre, t);
-      total = segsum_combine(total, t);
+    if (warp == 0)
+    { // the warp totals are scanned by one warp (not combined one after the other by every thread): exclusive prefix per warp
+      Seg w = segsum_identity<K, AggR>();
+      if (lane < FIX_W) w = S.warpTot[lane];
+#pragma unroll
+      for (int d = 1; d < FIX_W; d <<= 1)
+      {
+        const Seg o = shfl_up_t(w, d);
+        if (lane >= d) w = segsum_combine(o, w);
+      }
+      Seg wex = shfl_up_t(w, 1);
+      if (lane == 0) wex = segsum_identity<K, AggR>();
+      if (lane < FIX_W) S.warpTot[lane] = wex;
+      if (lane == FIX_W - 1) S.scanTot = w;
     }
+    __syncthreads();
+    const Seg pre = S.warpTot[warp];
+    total = S.scanTot;
     __syncthreads();
     return segsum_combine(pre, ex);
   }
@@ -799,7 +809,7 @@ __device__ __forceinline__ void enc_fix_tickets(const EncBufs &B, typename EncCt
 }
 
 template <int W, int BA, int V, class SymT>
-__global__ void __launch_bounds__(FIX_T, 1) k_enc_fix(const EncBufs B, int startDirty, int maxRounds)
+__global__ void __launch_bounds__(FIX_T, 1) k_enc_fix(const EncBufs B, int startDirty, int maxRounds, int followHops)
 {
   using C = EncCta<W, BA, V, SymT>;
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -859,20 +869,42 @@ __global__ void __launch_bounds__(FIX_T, 1) k_enc_fix(const EncBufs B, int start
       __threadfence();                                  // helpers on other SMs rewrote summaries: nothing stale may be read from this SM's L1
     }
     else
-    { // solo round: one dirty super-chunk per warp.  (Following a changed outgoing state through the next super-chunks inside
-      // the round was measured twice -- r01 with claims, r02 without: rounds drop from 58 / 90 to 3 / 14 for rle8_3symlut /
-      // rle8_7symlut on the DCT stream, but the time does not (4.2 ms) or triples (33 ms): the cost is the one-warp re-run of
-      // a super-chunk, ~70 us, and followers re-run super-chunks a later verify invalidates again.)
+    { // solo round: one dirty super-chunk per warp -- and the warp FOLLOWS what its re-run changed for a few super-chunks: while the
+      // outgoing state differs from the one the verify scan handed to the next super-chunk, that one takes the new state (re-run if
+      // its decisions depend on the difference, passed through otherwise), until the states coalesce, the next listed super-chunk
+      // is reached (its owner started from the scan's state: the next verify sorts that out) or the hop budget is spent.
       const uint32_t nl = min(S.nList, (uint32_t)FIX_LIST);
       const bool listed = S.nList <= (uint32_t)FIX_LIST;
       __syncthreads();
       for (uint32_t i = warp; i < (listed ? nl : nSC); i += FIX_W)
       {
-        const uint32_t s = listed ? S.list[i] : i;
+        uint32_t s = listed ? S.list[i] : i;
         if (!listed && !B.scDirty[s]) continue;
-        AutoState g = B.scIn[s]; typename C::LutR gl; if (C::K) lut_from(gl, B.scLut[s]); else lut_init(gl, W);
-        typename C::Seg tot;
-        C::process(B, S.r[warp], s, true, g, gl, tot, true);
+        AutoState xs = B.scIn[s]; typename C::LutR xl; if (C::K) lut_from(xl, B.scLut[s]); else lut_init(xl, W);
+        for (int hop = 0; hop < followHops; hop++)
+        {
+          typename C::Seg tot;
+          C::process(B, S.r[warp], s, true, xs, xl, tot, true);
+          if (hop + 1 == followHops) break;
+          segsum_apply(xs, xl, tot);                                   // (xs, xl): the new outgoing state
+          bool rerun = false;
+          for (s++; s < nSC; s++)
+          {
+            if (B.scDirty[s]) break;                                   // listed this round: not ours
+            const AutoState os = B.scIn[s];
+            bool lutDiff = false;
+            if (C::K) { typename C::LutR ol; lut_from(ol, B.scLut[s]); lutDiff = !lut_equal(ol, xl, C::K); }
+            if (os == xs && !lutDiff) break;                           // coalesced with what the scan assumed
+            rerun = (os != xs) || (lutDiff && C::lut_sensitive(B, s, xl));
+            __syncwarp();
+            if (lane == 0) { B.scIn[s] = xs; if (C::K) lut_to(B.scLut[s], xl); }
+            __syncwarp();
+            if (rerun) break;
+            const typename C::Seg e = C::load_seg(B, s, 0);            // decisions unaffected: the state passes through
+            segsum_apply(xs, xl, e);
+          }
+          if (!rerun) break;
+        }
       }
       __threadfence_block();
       __syncthreads();
