@@ -129,6 +129,12 @@ static int enc_follow_hops()
   static const int v = getenv("HSRLE_FOLLOW") ? std::max(1, atoi(getenv("HSRLE_FOLLOW"))) : 1;
   return v;
 }
+// HSRLE_LUTWALK=0 switches the stretch walk of the 8-bit LUT codecs off (experiments; the result is the same either way)
+static bool lut_walk_enabled()
+{
+  static const bool v = !(getenv("HSRLE_LUTWALK") && atoi(getenv("HSRLE_LUTWALK")) == 0);
+  return v;
+}
 static int enc_fix_grid(const EncBufs &B, int sms)
 {
   return B.maxSC <= 4 * FIX_SOLO ? 1 : std::min<int>(sms, 1 + (int)(B.maxSC / 64));
@@ -150,13 +156,20 @@ static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t
   B.tileStatus = cv.take<unsigned long long>(2 * (size_t)B.nTiles + 2);
   if (zeroBytes) *zeroBytes = cv.off;
   B.runA = cv.take<uint32_t>(B.maxRuns); B.runB = cv.take<uint32_t>(B.maxRuns);
-  B.runSym = cv.take<uint64_t>(sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns);
+  B.runSym = cv.take<uint64_t>((sp.W <= 4 ? ((size_t)B.maxRuns + 1) / 2 : (size_t)B.maxRuns) + 8);   // (+8: k_enc_lut_stretch reads whole 16-record groups)
   B.cIn = cv.take<AutoState>(maxChunks); B.cLut = cv.take<Lut>(sp.K ? maxChunks : 1); B.cKnown = cv.take<uint8_t>(sp.K ? maxChunks : 1);
   B.scFo = cv.take<Lut>(sp.K ? B.maxSC : 1); B.scFlags = cv.take<uint8_t>(sp.K ? B.maxSC : 1); B.scQ = cv.take<ScQueries>(sp.K ? B.maxSC : 1);
   B.scIn = cv.take<AutoState>(B.maxSC); B.scLut = cv.take<Lut>(sp.K ? B.maxSC : 1);
   B.scSum = cv.take<ChunkSum>(B.maxSC); B.scAgg = cv.take<LutAgg>(sp.K ? B.maxSC : 1);
   B.scBytes = cv.take<uint64_t>(B.maxSC); B.scTok = cv.take<uint32_t>(B.maxSC); B.scBase = cv.take<uint64_t>(B.maxSC);
   B.scDirty = cv.take<uint8_t>(B.maxSC);
+  if (sp.K && sp.W == 1)
+  { // stretch walk (hsrle_enc_lutwalk.cuh)
+    const size_t nBlk = (size_t)B.maxRuns / LW_BLK + 2;
+    B.lwPool = cv.take<LwDesc>(LW_CAP); B.lwOrd = cv.take<LwDesc>(LW_CAP);
+    B.lwBlkOff = cv.take<uint32_t>(nBlk); B.lwBlkCnt = cv.take<uint32_t>(nBlk);
+    B.scGuess = cv.take<uint64_t>(B.maxSC);
+  }
   B.bigList = cv.take<CopyDesc>((size_t)n / BIG_COPY + 4);
   B.medList = cv.take<CopyDesc>((size_t)n / MED_COPY + 4);
   return cv.off + 256;
@@ -187,6 +200,7 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.cnt = cv.take<DecCounters>(1);
   D.segCount = cv.take<uint32_t>((size_t)D.nSeg + 1);
   D.anchorAt = cv.take<uint32_t>((size_t)D.nChunks + 1);
+  D.skipFlag = cv.take<uint8_t>((size_t)D.nChunks + 1);
   D.flagAgg = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.bigCap = (uint32_t)(((size_t)outSize / ((size_t)DEC_TILE * DEC_HUGE_TILES)) + 64);      // every such operation covers at least 256 KiB of output
   D.bigList = cv.take<DecBigOp>(D.bigCap);                                                  // (their `ready` words must start as 0)
@@ -195,6 +209,7 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.chunkTab = cv.take<uint16_t>((size_t)D.nChunks * DEC_CB);
   D.sufMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WINC);
   D.chunkEntry = cv.take<uint32_t>((size_t)D.nChunks + 1);
+  D.liveList = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.subMap = cv.take<uint16_t>((size_t)D.nChunks * DEC_NSUB * DEC_WIN);
   D.aggBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes); D.incBuf = cv.take<uint8_t>(((size_t)D.nChunks + 1) * aggBytes);
   return cv.off + 256;
@@ -246,6 +261,12 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   const int sms = num_sms();
   HSRLE_LAUNCH_NAMED("k_enc_scan", k->scan, B.nTiles, E1_T, 0, st, B);
+  if (k->lutStretch && lut_walk_enabled())
+  { // 8-bit LUT codecs: the table at every super-chunk start, from the stretch walk
+    const int g = (int)std::min<uint64_t>((uint64_t)B.maxRuns / LW_BLK + 1, (uint64_t)sms * 8);
+    HSRLE_LAUNCH_NAMED("k_enc_lut_stretch", k->lutStretch, g, LW_T, 0, st, B);
+    HSRLE_LAUNCH_NAMED("k_enc_lut_walk", k->lutWalk, 1, LW_T, 0, st, B);
+  }
   const int autoGrid = (int)std::min<uint64_t>((uint64_t)B.maxSC, (uint64_t)sms * 6);
   HSRLE_LAUNCH_NAMED("k_enc_auto", k->autom, autoGrid, E2_T, k->autoSmem, st, B);
   HSRLE_LAUNCH_NAMED("k_enc_fix", k->fix, enc_fix_grid(B, sms), FIX_T, k->fixSmem, st, B, 0, enc_rounds(sp.W, sp.K), enc_follow_hops());

@@ -67,6 +67,8 @@ struct DecCounters                        // zeroed per call
   uint32_t emitBad, endSeen;              // K2: unparsable token on the true chain / terminator seen
   uint32_t nBig;                          // grid-wide operations registered
   uint32_t nTok;
+  uint32_t nLive;                         // K1 resolver: chunks in which a true token starts (entries of liveList)
+  uint32_t pad0;
   unsigned long long outTotal;            // output bytes of all tokens
 };
 
@@ -191,11 +193,13 @@ struct DecBufs
   DecCounters *cnt;         // --- zeroed per call from here ...
   uint32_t *segCount;       // [nSeg]    chunks of the segment that published their rows
   uint32_t *anchorAt;       // [nChunks] position of the first true token start the resolver saw in the chunk (0: none)
+  uint8_t *skipFlag;        // [nChunks] 1: the scout saw a true token jump over the whole chunk -- no table, no rows were written for it
   uint32_t *flagAgg;        // [nChunks] look-back: 1 = aggregate published, 2 = inclusive prefix published   ... to here
   uint16_t *chunkTab;       // [nChunks][DEC_CB]  exit code of the chunk for EVERY entry offset (read at the few offsets the chain visits)
   uint32_t *sufMap;         // [nChunks][DEC_WINC] absolute exit of the SEGMENT (or the first out-of-window landing inside it) per window offset
   uint16_t *subMap;         // [nChunks][DEC_NSUB][DEC_WIN] exit codes of the sub-chunks
   uint32_t *chunkEntry;     // [nChunks] first true token start of the chunk (POS_NONE: none) -- written by the resolver, read by K2
+  uint32_t *liveList;       // [cnt.nLive] the chunks with an entry, in stream order: K2's ticket / look-back order
   void *aggBuf, *incBuf;    // [nChunks] DecAgg<K>: per-chunk totals / inclusive prefixes
   DecBigOp *bigList;
   uint32_t bigCap;

@@ -258,7 +258,7 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
           if (c == g * DEC_SEG) pos = rows[(g - g0) * DEC_WINC + o];
           else pos = __ldcg(D.sufMap + (size_t)c * DEC_WINC + o);
         }
-        else pos = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + o), c * DEC_CB, single, clen);   // after a long literal
+        else pos = __ldcg(D.skipFlag + c) ? POS_BAD : dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + o), c * DEC_CB, single, clen);   // after a long literal
       }
       S.pos = pos;
       if (fin) S.done = 1; else S.gBase = pos / DEC_CB / DEC_SEG;
@@ -282,9 +282,28 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
       if (x < POS_SPECIAL && x / DEC_CB == c)
       {
         e = x;
-        x = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + (x - c * DEC_CB)), c * DEC_CB, single, clen);
+        x = __ldcg(D.skipFlag + c) ? POS_BAD : dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + (x - c * DEC_CB)), c * DEC_CB, single, clen);
       }
       D.chunkEntry[c] = e;
+    }
+  }
+  __syncthreads();
+  // the LIVE chunks (a true token starts in them), in stream order: K2 takes its tickets over this list -- the chunks inside
+  // long literals (all but one of an incompressible 1-GiB frame) cost it nothing
+  {
+    const uint32_t per = (nChunks + DM_T - 1) / DM_T;
+    const uint32_t lo = min(nChunks, (uint32_t)t * per), hi = min(nChunks, lo + per);
+    uint32_t mine = 0;
+    for (uint32_t c = lo; c < hi; c++) if (__ldcg(D.chunkEntry + c) < POS_SPECIAL) mine++;
+    rows[t] = mine;
+    __syncthreads();
+    uint32_t off = 0, total = 0;
+    for (int k = 0; k < DM_T; k++) { const uint32_t x = rows[k]; if (k < t) off += x; total += x; }
+    for (uint32_t c = lo; c < hi; c++) if (__ldcg(D.chunkEntry + c) < POS_SPECIAL) D.liveList[off++] = c;
+    if (t == 0)
+    {
+      if (total == 0) { D.liveList[0] = 0; total = 1; }               // (broken chain: K2 still has to settle the result)
+      D.cnt->nLive = total;
     }
   }
 }
@@ -308,15 +327,6 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   const int t = threadIdx.x;
   uint16_t *const ex = S.ex;
   const uint32_t availSC = clen - c0;                                 // stream bytes from the start of the chunk
-  // ---- the chunk image: one bulk copy (rounded up to 16 bytes: the caller's buffer is readable up to the next 16-byte
-  //      boundary after the stream, include/hsrle_b200.h)
-  if (t == 0)
-  {
-    mbar_init(&S.mbar, 1);
-    const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
-    mbar_expect_tx(&S.mbar, bytes);
-    bulk_load(S.img, D.in + c0, bytes, &S.mbar);
-  }
   // Scout: the first tokens of the TRUE chain can be followed from the stream start without any table as long as each
   // of them jumps over whole chunks (incompressible input is one token with a literal of the whole input).  A chunk such a
   // token jumps over holds no token start: its rows only have to be safe for the speculative chains that land in it.
@@ -336,19 +346,27 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
       }
       S.flag = skip;
     }
-    __syncthreads();                                                  // (also: mbarrier initialised before anybody waits)
+    __syncthreads();
   }
   const bool skipped = S.flag != 0;
-  if (!mbar_wait(&S.mbar, 0)) D.cnt->chainBad = 0x100;               // the copy must have landed before the area is reused
-  __syncthreads();
   if (skipped)
-  {
-    const uint32_t bad2 = EX_BAD | (EX_BAD << 16);
-    uint4 *dst = reinterpret_cast<uint4 *>(D.chunkTab + (size_t)c * DEC_CB);
-    for (uint32_t q = t; q < DEC_CB / 8; q += DM_T) dst[q] = make_uint4(bad2, bad2, bad2, bad2);
+  { // no table, no rows, no image: one flag (every reader of the chunk table checks it: dec_tab_skip)
+    if (t == 0) D.skipFlag[c] = 1;
   }
   else
   {
+    // ---- the chunk image: one bulk copy (rounded up to 16 bytes: the caller's buffer is readable up to the next 16-byte
+    //      boundary after the stream, include/hsrle_b200.h)
+    if (t == 0)
+    {
+      mbar_init(&S.mbar, 1);
+      const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
+      mbar_expect_tx(&S.mbar, bytes);
+      bulk_load(S.img, D.in + c0, bytes, &S.mbar);
+    }
+    __syncthreads();                                                  // mbarrier initialised before anybody waits
+    if (!mbar_wait(&S.mbar, 0)) D.cnt->chainBad = 0x100;
+    __syncthreads();
     // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
     //      words give the four 24-byte windows); raw code = where that token ends
     {
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     for (uint32_t i = t; i < nHere * DEC_WINC; i += DM_T)
     {
       const uint32_t ci = cFirst + i / DEC_WINC, w = i % DEC_WINC;
-      rows[i] = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)ci * DEC_CB + w), ci * DEC_CB, single, clen);
+      rows[i] = __ldcg(D.skipFlag + ci) ? POS_BAD : dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)ci * DEC_CB + w), ci * DEC_CB, single, clen);
     }
     __syncthreads();
     const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_CB;
@@ -789,6 +807,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   }
   const uint32_t clen = hs.clen, n = hs.n;
   const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB;
+  const uint32_t nLive = cnt.nLive;                                   // (K1's resolver)
   const bool single = hs.single != 0;
   const uint8_t *__restrict__ in = D.in;
   uint8_t *__restrict__ out = D.out;
@@ -801,10 +820,15 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
 #else
 #define HSRLE_DBG(code) do { } while (0)
 #endif
-  // phase timers (HSRLE_DEBUG): thread 0 sums the clock ticks between phase marks; dbg[3000 + phase] gets the totals (in 64-tick units)
+  // phase timers (build with -DHSRLE_PHASE_TIMERS, run with HSRLE_DEBUG): thread 0 sums the clock ticks between phase marks;
+  // dbg[3000 + phase] gets the totals (in 64-tick units).  Not in production builds: the counters cost registers.
+#if defined(HSRLE_PHASE_TIMERS)
   unsigned long long tPh[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   long long tLast = D.dbg ? clock64() : 0;
 #define HSRLE_PH(ph) do { if (D.dbg && t == 0) { const long long now_ = clock64(); tPh[ph] += (unsigned long long)(now_ - tLast); tLast = now_; } } while (0)
+#else
+#define HSRLE_PH(ph) do { } while (0)
+#endif
 
   // block-wide exclusive scan of (output bytes, last explicit symbol) over the threads; totals returned in (totOut, totSym)
   auto block_scan = [&](unsigned long long myOut, uint32_t mySym, unsigned long long &exOut, uint32_t &exSym, unsigned long long &totOut, uint32_t &totSym)
@@ -832,8 +856,9 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     __syncthreads();
     if (t == 0) { S.ticket = atomicAdd(&cnt.ticket, 1u); }
     __syncthreads();
-    const uint32_t c = S.ticket;
-    if (c >= nChunks) break;
+    const uint32_t slot = S.ticket;                                   // position in the list of live chunks (look-back order)
+    if (slot >= nLive) break;
+    const uint32_t c = __ldcg(D.liveList + slot);
     const uint32_t c0 = c * DEC_CB;
     const uint32_t availSC = clen - c0;
     HSRLE_DBG(0x1000000u | c);
@@ -1028,10 +1053,10 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
 #pragma unroll
         for (int i = 0; i < 7; i++) if (i < K) tot.xf.e[i] = __shfl_sync(0xFFFFFFFFu, inc.xf.e[i], 31);
       }
-      if (lane == 0) { decagg_store<K>(&aggBuf[c], tot); st_release_u32(D.flagAgg + c, 1u); }
+      if (lane == 0) { decagg_store<K>(&aggBuf[slot], tot); st_release_u32(D.flagAgg + slot, 1u); }
     }
     Agg excl = decagg_identity<K>();                                  // (maintained by warp 0)
-    for (int64_t base = (int64_t)c - 1; base >= 0; base -= DX_T)
+    for (int64_t base = (int64_t)slot - 1; base >= 0; base -= DX_T)
     {
       const int64_t p = base - t;
       uint32_t fl = 2u;                                               // threads before chunk 0 behave like an (identity) inclusive prefix
@@ -1078,8 +1103,8 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       const Agg incl = decagg_combine<K>(excl, tot);
       if (lane == 0)
       {
-        decagg_store<K>(&incBuf[c], incl); st_release_u32(D.flagAgg + c, 2u);
-        if (c == nChunks - 1) { cnt.outTotal = incl.out; cnt.nTok = incl.ntok; }
+        decagg_store<K>(&incBuf[slot], incl); st_release_u32(D.flagAgg + slot, 2u);
+        if (slot == nLive - 1) { cnt.outTotal = incl.out; cnt.nTok = incl.ntok; }
         decagg_store<K>(&S.bc, excl);
         if (!K) S.inSym = single ? (uint64_t)hs.singleSym : (excl.symPos ? load_sym(in + excl.symPos, W) : 0ull);
       }
@@ -1241,7 +1266,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
     if (t == 0)
     {
       __threadfence();
-      if (atomicAdd(&cnt.chunksDone, 1u) == nChunks - 1)
+      if (atomicAdd(&cnt.chunksDone, 1u) == nLive - 1)
       {
         __threadfence();
         uint32_t status = ST_OK;
@@ -1255,7 +1280,9 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
   }
 
   HSRLE_PH(10);
+#if defined(HSRLE_PHASE_TIMERS)
   if (D.dbg && t == 0) { for (int i = 0; i < 12; i++) atomicAdd(D.dbg + 3000 + i, (uint32_t)(tPh[i] >> 6)); }
+#endif
   // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken.  One thread
   //      polls (the others wait at the barrier and cost no issue slots).
   uint32_t seenBig = 0;
@@ -1267,7 +1294,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
       uint32_t done, nb, spin = 0;
       for (;;)
       {
-        done = (ld_volatile_u32(&cnt.chunksDone) >= nChunks) ? 1u : 0u;
+        done = (ld_volatile_u32(&cnt.chunksDone) >= nLive) ? 1u : 0u;
         __threadfence();
         nb = min(ld_volatile_u32(&cnt.nBig), D.bigCap);
         if (done || nb > seenBig || ++spin > (1u << 22)) break;

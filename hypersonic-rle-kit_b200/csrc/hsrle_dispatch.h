@@ -13,6 +13,8 @@ struct EncKernels
   void (*autom)(const EncBufs);
   void (*fix)(const EncBufs, int, int, int);
   void (*emit)(const EncBufs);
+  void (*lutStretch)(const EncBufs);   // 8-bit LUT codecs only (hsrle_enc_lutwalk.cuh), else null
+  void (*lutWalk)(const EncBufs);
   size_t autoSmem, fixSmem, emitSmem;
   int symBytes;           // 4 or 8: element size of EncBufs::runSym
   int minM;

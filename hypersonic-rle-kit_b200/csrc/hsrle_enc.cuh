@@ -71,9 +71,11 @@ struct EncScalars
   uint32_t fixCmd, fixRound, fixTicket, fixDone;   // k_enc_fix: helpers leave / grid round number / ticket counter / tickets completed
   uint32_t endShift;                      // slices: start record i pairs with end record i + endShift (hsrle_slice.cuh)
   uint32_t nStarts, nEnds;                // slices: records found by the scan
+  uint32_t lwCount, lwOverflow, lwOk;     // 8-bit LUT codecs (hsrle_enc_lutwalk.cuh): stretch boundaries found / too many or too long / scGuess is valid
 };
 
 struct CopyDesc { uint32_t dst, src, len; };
+struct LwDesc;
 
 // LUT codecs: the decisions of a super-chunk that consulted the part of the table it inherited (marginal candidates whose
 // symbol had not been emitted inside the super-chunk yet): symbol, how many first emissions (scFo) preceded it, and the
@@ -137,6 +139,9 @@ struct EncBufs
   ScQueries *scQ;                        // LUT codecs: the table queries behind SCF_SENS
   uint64_t *scBase;                      // per super-chunk: exclusive token-byte offset
   uint8_t *scDirty;
+  LwDesc *lwPool, *lwOrd;                // 8-bit LUT codecs: stretch-boundary descriptors as found / in record order,
+  uint32_t *lwBlkOff, *lwBlkCnt;         //   where every block of LW_BLK records put its own,
+  uint64_t *scGuess;                     //   and the walk's result: the (packed) table at every super-chunk start
   CopyDesc *bigList, *medList;
   EncScalars *sc;
   uint32_t *dResult;

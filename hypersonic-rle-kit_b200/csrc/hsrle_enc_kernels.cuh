@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <type_traits>
 #include "hsrle_enc.cuh"
+#include "hsrle_enc_lutwalk.cuh"
 #include "hsrle_slice.cuh"
 
 namespace hsrle {
@@ -425,6 +426,8 @@ template <int W, int BA, int V, class SymT> struct EncCta
       const int w0 = max(j0 - E2_WARM, E2_WARM - halo);
       enc_neutral_state(sp, (active && w0 < j0) ? R.a[w0 + w0 / E2L_CH] : 0u, stIn, lutIn);
       if (active && w0 < j0) { AutoState ws = stIn; LutR wl = lutIn; (void)eval_range<E2L_CH>(R.a, R.b, R.sym, n, floor, w0, j0, ws, wl); stIn = ws; lutIn = wl; }
+      // 8-bit LUT codecs: the table at the super-chunk start comes from the stretch walk (hsrle_enc_lutwalk.cuh) when it ran
+      if constexpr (K != 0 && W == 1) { if (lane == 0 && !given && B.sc->lwOk) lutIn.v = B.scGuess[s]; }
     }
     Seg mine = segsum_identity<K, AggR>();
     uint32_t sens0 = 0;

@@ -16,6 +16,8 @@ template <int W, int BA, int V> static EncKernels make_enc_kernels()
   k.autom = &k_enc_auto<W, BA, V, SymT>;
   k.fix = &k_enc_fix<W, BA, V, SymT>;
   k.emit = &k_enc_emit<W, BA, V, SymT>;
+  k.lutStretch = nullptr; k.lutWalk = nullptr;
+  if constexpr (W == 1 && sp.K != 0) { k.lutStretch = &k_enc_lut_stretch<V>; k.lutWalk = &k_enc_lut_walk<V>; }
   k.autoSmem = sizeof(typename C::Smem);
   k.fixSmem = sizeof(typename C::FixSmem);
   k.emitSmem = sizeof(EncEmitSmem<W, BA, V, SymT>);
@@ -45,7 +47,7 @@ const EncKernels *HSRLE_CAT(enc_kernels_w, HSRLE_INST_W)()
   static bool init = false;
   if (!init)
   {
-    for (int i = 0; i < 8; i++) tab[i] = EncKernels{ nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < 8; i++) tab[i] = EncKernels{ nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0 };
     constexpr int W = HSRLE_INST_W;
     if constexpr (W > 1)
     {

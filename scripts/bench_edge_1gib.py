@@ -38,9 +38,16 @@ for kind in ("single_symbol", "random", "alternating", "run_mixed"):
         for _ in range(reps): hs.decompress_device_async(name, t_out, r, t_dec, n, ws, res[8:], sp)
         ev[2].record(); torch.cuda.synchronize()
         te, td = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        import ctypes
+        buf = ctypes.create_string_buffer(8192)
+        hs.lib.hsrle_timing_begin()
+        hs.compress_device_async(name, t_in, t_out, ws, res[:8], sp)
+        hs.decompress_device_async(name, t_out, r, t_dec, n, ws, res[8:], sp)
+        hs.lib.hsrle_timing_end(buf, 8192)
+        kt = {p.split(':')[0][2:]: round(1e3 * float(p.split(':')[2])) for p in buf.value.decode().split(";") if p}
         print(json.dumps({"input": kind, "codec": name, "n": n, "stream_bytes": r, "enc_ms": round(te, 3), "dec_ms": round(td, 3),
                           "enc_GBps": round(n / te / 1e6, 1), "dec_GBps": round(n / td / 1e6, 1),
                           "enc_roofline": round((n + r) / te / 1e6 / 6551.4, 3), "dec_roofline": round((n + r) / td / 1e6 / 6551.4, 3),
-                          "roundtrip_ok": bool(torch.equal(t_dec[:n], t_in))}), flush=True)
+                          "roundtrip_ok": bool(torch.equal(t_dec[:n], t_in)), "kernel_us": kt}), flush=True)
         del ws, t_out, t_dec
     del t_in
