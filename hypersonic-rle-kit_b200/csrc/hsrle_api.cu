@@ -202,8 +202,10 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.anchorAt = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.skipFlag = cv.take<uint8_t>((size_t)D.nChunks + 1);
   D.flagAgg = cv.take<uint32_t>((size_t)D.nChunks + 1);
-  D.bigCap = (uint32_t)(((size_t)outSize / ((size_t)DEC_TILE * DEC_HUGE_TILES)) + 64);      // every such operation covers at least 256 KiB of output
+  D.bigCap = (uint32_t)(((size_t)outSize / ((size_t)DEC_TILE * DEC_HUGE_TILES)) + 64);      // every such operation covers at least 64 KiB of output
   D.bigList = cv.take<DecBigOp>(D.bigCap);                                                  // (their `ready` words must start as 0)
+  D.pieceCap = (uint32_t)((size_t)outSize / DEC_BIG_PIECE) + D.bigCap + 64;                 // whole pieces + one partial piece per operation
+  D.pieceOp = cv.take<uint32_t>(D.pieceCap);
   if (zeroBytes) *zeroBytes = cv.off;
   D.sc = cv.take<DecScalars>(1);
   D.chunkTab = cv.take<uint16_t>((size_t)D.nChunks * DEC_CB);
@@ -384,15 +386,17 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   D.emitGrid = (uint32_t)g_emitGrid[current_dev()][codec];
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   static const bool dbg = getenv("HSRLE_DEBUG") != nullptr;
-  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, D.nChunks, DM_T, k->mapSmem, st, D);
-  if (dbg) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[hsrle] k_dec_map done: %s (chunks %u)\n", cudaGetErrorString(e), D.nChunks); fflush(stderr); }
   static uint32_t *hDbg = nullptr;
   if (dbg)
   {
     if (!hDbg) cudaHostAlloc((void **)&hDbg, 4096 * 4, cudaHostAllocMapped);
     memset(hDbg, 0, 4096 * 4);
     cudaHostGetDevicePointer((void **)&D.dbg, hDbg, 0);
+    for (int i = 3000; i < 3200; i++) hDbg[i] = 0;
   }
+  // (CTAs loop over chunks: the scout runs once per CTA, and the chunks it rules out cost a flag each)
+  HSRLE_LAUNCH_NAMED("k_dec_map", k->map, std::min<uint32_t>(D.nChunks, (uint32_t)num_sms() * 8u), DM_T, k->mapSmem, st, D);
+  if (dbg) { cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "[hsrle] k_dec_map done: %s (chunks %u)\n", cudaGetErrorString(e), D.nChunks); fflush(stderr); }
   HSRLE_LAUNCH_NAMED("k_dec_emit", k->emit, D.emitGrid, DX_T, k->emitSmem, st, D);
   if (dbg)
   {
@@ -408,7 +412,7 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
     }
     fprintf(stderr, "[hsrle] k_dec_emit done: %s (grid %u); phase ticks/64:", cudaGetErrorString(cudaStreamSynchronize(st)), D.emitGrid);
     for (int i = 0; i < 12; i++) fprintf(stderr, " %u", hDbg[3000 + i]);
-    fprintf(stderr, "\n"); fflush(stderr);
+    fprintf(stderr, " | K1 resolver ns: chain %u, entries %u, live list %u\n", hDbg[3100], hDbg[3101], hDbg[3102]); fflush(stderr);
   }
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }

@@ -41,7 +41,7 @@ constexpr uint32_t DEC_SEG = 16;          // chunks per segment
 constexpr uint32_t DEC_IMG_PAD = 512;     // stream bytes loaded after the chunk (token heads and short literals that straddle its end)
 constexpr uint32_t DEC_TILE = 16384;      // output image bytes per expansion step
 constexpr uint32_t DEC_NSLOT = 1024;      // token records per expansion pass
-constexpr uint32_t DEC_HUGE_TILES = 16;   // a token part covering at least this many whole tiles is a grid-wide operation
+constexpr uint32_t DEC_HUGE_TILES = 4;    // a token part covering at least this many whole tiles is a grid-wide operation
 constexpr uint32_t DEC_BIG_PIECE = 65536; // bytes of a grid-wide operation one CTA takes at a time
 
 constexpr uint32_t POS_END = 0xFFFFFFFFu; // chain reached the terminator
@@ -65,10 +65,11 @@ struct DecCounters                        // zeroed per call
   uint32_t chainBad;                      // K1 resolver: the true chain does not reach the terminator
   uint32_t ticket, chunksDone;            // K2: dynamic chunk ids, chunks finished
   uint32_t emitBad, endSeen;              // K2: unparsable token on the true chain / terminator seen
-  uint32_t nBig;                          // grid-wide operations registered
+  uint32_t nBig;                          // grid-wide operations registered (for the result words)
+  uint32_t bigTicket;                     // pieces of grid-wide operations handed out
   uint32_t nTok;
   uint32_t nLive;                         // K1 resolver: chunks in which a true token starts (entries of liveList)
-  uint32_t pad0;
+  unsigned long long bigReg;              // operations registered << 40 | their pieces: one atomic numbers both consistently
   unsigned long long outTotal;            // output bytes of all tokens
 };
 
@@ -78,7 +79,7 @@ struct DecBigOp
 {
   uint64_t sym;
   uint32_t dst, len, src, kind;
-  uint32_t next;                          // pieces handed out
+  uint32_t pieceBase;                     // number of the operation's first piece in the global piece order
   uint32_t ready;                         // published
 };
 
@@ -203,6 +204,8 @@ struct DecBufs
   void *aggBuf, *incBuf;    // [nChunks] DecAgg<K>: per-chunk totals / inclusive prefixes
   DecBigOp *bigList;
   uint32_t bigCap;
+  uint32_t *pieceOp;        // [pieceCap] (zeroed) piece number -> operation index + 1, written when the operation is registered
+  uint32_t pieceCap;
   uint32_t *dResult;
   uint32_t *dbg;            // debugging aid (HSRLE_DEBUG): host-mapped stage markers, one word per CTA of K2; null otherwise
 };

@@ -189,6 +189,7 @@ struct DecMapSmem
   alignas(16) uint16_t ex[DEC_EXH_ELEMS];           // per-position exit codes (skewed)
   alignas(8) unsigned long long mbar;
   uint32_t flag, pos, gBase, done;
+  uint32_t nScout, scP[DM_SCOUT], scN[DM_SCOUT];     // the scout's jumps: token start, next token start
 };
 static_assert(DEC_IMG_BYTES % 16 == 0 && DEC_IMG_BYTES + DEC_EXH_ELEMS * 2 >= DM_STAGE_ROWS * DEC_WINC * 4, "rows fit the image + table area");
 static_assert(DEC_SEG * DEC_WINC * 4 <= DEC_IMG_BYTES + DEC_EXH_ELEMS * 2, "segment rows fit");
@@ -227,6 +228,12 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
   const uint32_t clen = hs.clen;
   const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB, nSeg = (nChunks + DEC_SEG - 1) / DEC_SEG;
   const bool single = hs.single != 0;
+#if defined(HSRLE_PHASE_TIMERS)
+  unsigned long long rt0 = 0; if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(rt0));
+#define HSRLE_RT(i) do { if (D.dbg && t == 0) { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); D.dbg[3100 + (i)] = (uint32_t)(now_ - rt0); } } while (0)
+#else
+#define HSRLE_RT(i) do { } while (0)
+#endif
   if (t == 0) { S.pos = hs.first; S.gBase = 0; S.done = 0; }
   __syncthreads();
   uint32_t lastAnchor = 0xFFFFFFFFu;
@@ -269,6 +276,7 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
   if (t == 0 && S.pos != POS_END) D.cnt->chainBad = 1;
   __threadfence();
   __syncthreads();
+  HSRLE_RT(0);
   // every chunk's first true token start: one thread per segment walks its chunks through the chunk tables from the anchors
   for (uint32_t g = t; g < nSeg; g += DM_T)
   {
@@ -288,6 +296,7 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
     }
   }
   __syncthreads();
+  HSRLE_RT(1);
   // the LIVE chunks (a true token starts in them), in stream order: K2 takes its tickets over this list -- the chunks inside
   // long literals (all but one of an incompressible 1-GiB frame) cost it nothing
   {
@@ -306,6 +315,7 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
       D.cnt->nLive = total;
     }
   }
+  HSRLE_RT(2);
 }
 
 template <int W, int BA, int V>
@@ -318,39 +328,41 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   DecScalars hs; dec_header(sp, D.in, D.inSize, D.outSize, hs);
   if (blockIdx.x == 0 && threadIdx.x == 0) *D.sc = hs;
   if (hs.status != ST_OK) return;
-  const uint32_t c = blockIdx.x;
-  const uint32_t c0 = c * DEC_CB;
   const uint32_t clen = hs.clen;
-  if (c0 >= clen) return;
   const uint32_t nChunks = (clen + DEC_CB - 1) / DEC_CB, nSeg = (nChunks + DEC_SEG - 1) / DEC_SEG;
   const bool single = hs.single != 0;
   const int t = threadIdx.x;
   uint16_t *const ex = S.ex;
-  const uint32_t availSC = clen - c0;                                 // stream bytes from the start of the chunk
-  // Scout: the first tokens of the TRUE chain can be followed from the stream start without any table as long as each
-  // of them jumps over whole chunks (incompressible input is one token with a literal of the whole input).  A chunk such a
-  // token jumps over holds no token start: its rows only have to be safe for the speculative chains that land in it.
+  // Scout (once per CTA): the first tokens of the TRUE chain can be followed from the stream start without any table as long as
+  // each of them jumps over whole chunks (incompressible input is one token with a literal of the whole input).  A chunk such a
+  // token jumps over holds no token start: it gets a flag instead of a table.
+  if (t == 0)
   {
-    if (t == 0)
+    mbar_init(&S.mbar, 1);
+    uint32_t k = 0, p = hs.first;
+    for (int i = 0; i < DM_SCOUT; i++)
     {
-      uint32_t skip = 0, p = hs.first;
-      for (int i = 0; i < DM_SCOUT && p < c0; i++)
-      {
-        Tok tk; dec_parse(sp, single, D.in + p, (uint64_t)clen - p, tk);
-        if (!tk.valid) break;
-        if (tk.last) { skip = 1; break; }                             // the final token starts before this chunk: nothing starts in it
-        const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
-        if (nx >= (uint64_t)c0 + DEC_CB) { skip = 1; break; }         // starts before this chunk, next token after it
-        if (tk.litLen < 4 * DEC_CB) break;
-        p = (uint32_t)nx;
-      }
-      S.flag = skip;
+      Tok tk; dec_parse(sp, single, D.in + p, (uint64_t)clen - p, tk);
+      if (!tk.valid) break;
+      if (tk.last) { S.scP[k] = p; S.scN[k] = 0xFFFFFFFFu; k++; break; }   // nothing starts after the final token
+      const uint64_t nx = (uint64_t)p + tk.hdrLen + tk.litLen;
+      if (tk.litLen < 4 * DEC_CB) break;
+      S.scP[k] = p; S.scN[k] = (uint32_t)min(nx, (uint64_t)0xFFFFFFFFu); k++;
+      p = (uint32_t)nx;
     }
-    __syncthreads();
+    S.nScout = k;
   }
-  const bool skipped = S.flag != 0;
+  uint32_t phase = 0;
+  __syncthreads();                                                    // (also: mbarrier initialised before anybody waits)
+  for (uint32_t c = blockIdx.x; c < nChunks; c += gridDim.x)
+  {
+  const uint32_t c0 = c * DEC_CB;
+  const uint32_t availSC = clen - c0;                                 // stream bytes from the start of the chunk
+  bool skipped = false;
+  for (uint32_t i = 0; i < S.nScout; i++) skipped = skipped || (S.scP[i] < c0 && (uint64_t)S.scN[i] >= (uint64_t)c0 + DEC_CB);
+  __syncthreads();                                                    // the previous chunk's rows (they alias the image) are done with
   if (skipped)
-  { // no table, no rows, no image: one flag (every reader of the chunk table checks it: dec_tab_skip)
+  { // no table, no rows, no image: one flag (every reader of the chunk table checks it)
     if (t == 0) D.skipFlag[c] = 1;
   }
   else
@@ -359,13 +371,13 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     //      boundary after the stream, include/hsrle_b200.h)
     if (t == 0)
     {
-      mbar_init(&S.mbar, 1);
+      fence_async_smem();
       const uint32_t bytes = min(DEC_CB + DEC_IMG_PAD, (availSC + 15u) & ~15u);
       mbar_expect_tx(&S.mbar, bytes);
       bulk_load(S.img, D.in + c0, bytes, &S.mbar);
     }
-    __syncthreads();                                                  // mbarrier initialised before anybody waits
-    if (!mbar_wait(&S.mbar, 0)) D.cnt->chainBad = 0x100;
+    if (!mbar_wait(&S.mbar, phase)) D.cnt->chainBad = 0x100;
+    phase ^= 1u;
     __syncthreads();
     // ---- phase A: a token parse at EVERY byte offset, four consecutive offsets per thread and step (seven aligned
     //      words give the four 24-byte windows); raw code = where that token ends
@@ -493,8 +505,16 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   __syncthreads();
   if (t == 0) S.flag = (atomicAdd(D.segCount + g, 1u) == nHere - 1) ? 1u : 0u;
   __syncthreads();
-  if (!S.flag) return;
+  if (!S.flag) continue;
   __threadfence();
+  if (t == 0)
+  { // a segment of jumped-over chunks has no rows
+    uint32_t live = 0;
+    for (uint32_t i = 0; i < nHere; i++) live += __ldcg(D.skipFlag + cFirst + i) ? 0u : 1u;
+    S.pos = live;
+  }
+  __syncthreads();
+  if (S.pos != 0)
   {
     for (uint32_t i = t; i < nHere * DEC_WINC; i += DM_T)
     {
@@ -522,9 +542,10 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
   __syncthreads();
   if (t == 0) S.flag = (atomicAdd(&D.cnt->segsDone, 1u) == nSeg - 1) ? 1u : 0u;
   __syncthreads();
-  if (!S.flag) return;
+  if (!S.flag) continue;
   __threadfence();
   dec_resolve<W, BA, V>(D, hs, S, rows);
+  }
 }
 
 // ================================================================================================
@@ -1167,15 +1188,18 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
             if (kB < kA + DEC_HUGE_TILES) continue;
             const uint32_t slot = atomicAdd(&S.nSkip, 1u);
             if (slot >= (uint32_t)DX_NSKIP) continue;
-            const uint32_t idx = atomicAdd(&cnt.nBig, 1u);
-            if (idx >= D.bigCap) { S.skipLo[slot] = 0; S.skipHi[slot] = 0; continue; }
+            const uint32_t opLen = (uint32_t)((kB - kA) * DEC_TILE), np = (opLen + DEC_BIG_PIECE - 1) / DEC_BIG_PIECE;
+            const unsigned long long reg = atomicAdd(&cnt.bigReg, (1ull << 40) | (unsigned long long)np);
+            const uint32_t idx = (uint32_t)(reg >> 40), base = (uint32_t)(reg & 0xFFFFFFFFFFull);
+            if (idx >= D.bigCap || base + np > D.pieceCap) { cnt.emitBad = 0x800; S.skipLo[slot] = 0; S.skipHi[slot] = 0; continue; }   // (cannot happen: the caps are upper bounds)
             S.skipLo[slot] = (uint32_t)kA; S.skipHi[slot] = (uint32_t)kB;
             DecBigOp &op = D.bigList[idx];
-            op.dst = (uint32_t)(T0 + kA * DEC_TILE); op.len = (uint32_t)((kB - kA) * DEC_TILE); op.kind = (uint32_t)part; op.sym = part ? rec_sym(r) : 0ull;
+            op.dst = (uint32_t)(T0 + kA * DEC_TILE); op.len = opLen; op.kind = (uint32_t)part; op.sym = part ? rec_sym(r) : 0ull;
             op.src = part ? (uint32_t)m : (uint32_t)(c0 + S.rSrc[r] + (T0 + kA * DEC_TILE - a));
-            op.next = 0;
+            op.pieceBase = base;
             __threadfence();
             st_volatile_u32(&op.ready, 1u);
+            for (uint32_t k = 0; k < np; k++) st_volatile_u32(D.pieceOp + base + k, idx + 1u);
           }
         }
         __syncthreads();
@@ -1274,7 +1298,7 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
         const unsigned long long tot = ld_volatile_u64(&cnt.outTotal);
         if (bad || !end || tot != (unsigned long long)n) status = ST_BADSTREAM;
         D.dResult[0] = status == ST_OK ? n : 0; D.dResult[1] = status; D.dResult[2] = ld_volatile_u32(&cnt.nTok); D.dResult[3] = nChunks;
-        D.dResult[4] = clen; D.dResult[5] = hs.single; D.dResult[6] = ld_volatile_u32(&cnt.nBig); D.dResult[7] = bad;
+        D.dResult[4] = clen; D.dResult[5] = hs.single; D.dResult[6] = (uint32_t)(ld_volatile_u64(&cnt.bigReg) >> 40); D.dResult[7] = bad;
       }
     }
   }
@@ -1283,53 +1307,42 @@ __global__ void __launch_bounds__(DX_T) k_dec_emit(const DecBufs D)
 #if defined(HSRLE_PHASE_TIMERS)
   if (D.dbg && t == 0) { for (int i = 0; i < 12; i++) atomicAdd(D.dbg + 3000 + i, (uint32_t)(tPh[i] >> 6)); }
 #endif
-  // ---- grid-wide operations: every CTA without a chunk helps until all chunks are done and all pieces are taken.  One thread
-  //      polls (the others wait at the barrier and cost no issue slots).
-  uint32_t seenBig = 0;
+  // ---- grid-wide operations: every CTA that is out of chunks takes pieces (DEC_BIG_PIECE bytes each) in the global piece order until
+  //      all chunks are done and every registered piece is taken.  One atomic per piece; the operation a piece belongs to is looked up
+  //      in pieceOp (written at registration).  One thread polls (the others wait at the barrier and cost no issue slots).
   for (uint32_t guard = 0; guard < (1u << 24); guard++)
   {
     __syncthreads();
     if (t == 0)
-    { // "all done" is sampled before the operation count: whatever was registered before the last chunk finished is seen
-      uint32_t done, nb, spin = 0;
-      for (;;)
-      {
-        done = (ld_volatile_u32(&cnt.chunksDone) >= nLive) ? 1u : 0u;
+    {
+      const uint32_t T = atomicAdd(&cnt.bigTicket, 1u);
+      uint32_t found = 0, opi = 0;
+      for (uint32_t spin = 0; spin < (1u << 22); spin++)
+      { // "all done" is sampled before the registration count: whatever was registered before the last chunk finished is seen
+        const uint32_t done = (ld_volatile_u32(&cnt.chunksDone) >= nLive) ? 1u : 0u;
         __threadfence();
-        nb = min(ld_volatile_u32(&cnt.nBig), D.bigCap);
-        if (done || nb > seenBig || ++spin > (1u << 22)) break;
-        __nanosleep(1000);
+        const unsigned long long reg = ld_volatile_u64(&cnt.bigReg);
+        if (T < (uint32_t)(reg & 0xFFFFFFFFFFull)) { found = 1; break; }
+        if (done) break;
+        __nanosleep(500);
       }
-      S.flag = done; S.entry = nb;
+      if (found)
+      {
+        uint32_t spin = 0;
+        while ((opi = ld_volatile_u32(D.pieceOp + T)) == 0u && ++spin < (1u << 24)) { }
+        if (opi) { while (ld_volatile_u32(&D.bigList[opi - 1].ready) == 0u && ++spin < (1u << 24)) { } }
+        if (!opi || spin >= (1u << 24)) { cnt.emitBad = 0x900; found = 0; }
+      }
+      S.flag = found; S.entry = opi; S.bcast = T;
     }
     __syncthreads();
-    const bool allDone = S.flag != 0;
-    const uint32_t nb = S.entry;
+    if (!S.flag) break;
     __threadfence();
-    bool pending = false;
-    for (uint32_t i = 0; i < nb; i++)
-    {
-      DecBigOp &op = D.bigList[i];
-      __syncthreads();
-      if (t == 0) S.bcast = ld_volatile_u32(&op.ready);
-      __syncthreads();
-      if (!S.bcast) { pending = true; continue; }
-      __threadfence();
-      DecBigOp o;
-      o.sym = __ldcg(&op.sym); o.dst = __ldcg(&op.dst); o.len = __ldcg(&op.len); o.src = __ldcg(&op.src); o.kind = __ldcg(&op.kind);
-      const uint32_t np = (o.len + DEC_BIG_PIECE - 1) / DEC_BIG_PIECE;
-      for (;;)
-      {
-        __syncthreads();
-        if (t == 0) S.bcast = (ld_volatile_u32(&op.next) >= np) ? np : atomicAdd(&op.next, 1u);
-        __syncthreads();
-        const uint32_t k = S.bcast;
-        if (k >= np) break;
-        dec_big_piece<W, K>(D, S, o, k * DEC_BIG_PIECE, min(DEC_BIG_PIECE, o.len - k * DEC_BIG_PIECE), phase0, phase1);
-      }
-    }
-    if (!pending) seenBig = nb;
-    if (allDone && !pending) break;
+    const DecBigOp &op = D.bigList[S.entry - 1];
+    DecBigOp o;
+    o.sym = __ldcg(&op.sym); o.dst = __ldcg(&op.dst); o.len = __ldcg(&op.len); o.src = __ldcg(&op.src); o.kind = __ldcg(&op.kind);
+    const uint32_t k = S.bcast - __ldcg(&op.pieceBase);
+    dec_big_piece<W, K>(D, S, o, k * DEC_BIG_PIECE, min(DEC_BIG_PIECE, o.len - k * DEC_BIG_PIECE), phase0, phase1);
   }
 }
 

@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libhsrle_b200.so")
+# HSRLE_LIB picks another build of the same library (the diagnosis variant libhsrle_b200_dbg.so, see the Makefile)
+LIB_PATH = os.path.join(os.path.dirname(_HERE), os.environ.get("HSRLE_LIB", "libhsrle_b200.so"))
 
 _u8p = ctypes.POINTER(ctypes.c_uint8)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
