@@ -210,6 +210,7 @@ static size_t dec_carve(DecBufs &D, const Spec &sp, uint32_t inSize, uint32_t ou
   D.sc = cv.take<DecScalars>(1);
   D.chunkTab = cv.take<uint16_t>((size_t)D.nChunks * DEC_CB);
   D.sufMap = cv.take<uint32_t>((size_t)D.nChunks * DEC_WINC);
+  D.segTab = cv.take<uint32_t>((size_t)D.nChunks * DEC_CB);
   D.chunkEntry = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.liveList = cv.take<uint32_t>((size_t)D.nChunks + 1);
   D.subMap = cv.take<uint16_t>((size_t)D.nChunks * DEC_NSUB * DEC_WIN);
@@ -412,7 +413,7 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
     }
     fprintf(stderr, "[hsrle] k_dec_emit done: %s (grid %u); phase ticks/64:", cudaGetErrorString(cudaStreamSynchronize(st)), D.emitGrid);
     for (int i = 0; i < 12; i++) fprintf(stderr, " %u", hDbg[3000 + i]);
-    fprintf(stderr, " | K1 resolver ns: chain %u, entries %u, live list %u\n", hDbg[3100], hDbg[3101], hDbg[3102]); fflush(stderr);
+    fprintf(stderr, " | K1 resolver ns: chain %u, entries %u, live list %u | sparse composition: max ns %u, segments %u, far parses %u\n", hDbg[3100], hDbg[3101], hDbg[3102], hDbg[3110], hDbg[3111], hDbg[3112]); fflush(stderr);
   }
   return cuda_ok(cudaGetLastError(), "decode launch") ? 0 : 2;
 }

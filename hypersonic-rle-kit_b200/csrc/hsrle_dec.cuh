@@ -197,7 +197,8 @@ struct DecBufs
   uint8_t *skipFlag;        // [nChunks] 1: the scout saw a true token jump over the whole chunk -- no table, no rows were written for it
   uint32_t *flagAgg;        // [nChunks] look-back: 1 = aggregate published, 2 = inclusive prefix published   ... to here
   uint16_t *chunkTab;       // [nChunks][DEC_CB]  exit code of the chunk for EVERY entry offset (read at the few offsets the chain visits)
-  uint32_t *sufMap;         // [nChunks][DEC_WINC] absolute exit of the SEGMENT (or the first out-of-window landing inside it) per window offset
+  uint32_t *sufMap;         // dense streams: [nChunks][DEC_WINC] absolute exit of the SEGMENT (or the first out-of-window landing inside it) per window offset
+  uint32_t *segTab;         // sparse streams: [nChunks * DEC_CB] per stream position: where the chain through it leaves its SEGMENT (absolute / POS_END / POS_BAD)
   uint16_t *subMap;         // [nChunks][DEC_NSUB][DEC_WIN] exit codes of the sub-chunks
   uint32_t *chunkEntry;     // [nChunks] first true token start of the chunk (POS_NONE: none) -- written by the resolver, read by K2
   uint32_t *liveList;       // [cnt.nLive] the chunks with an entry, in stream order: K2's ticket / look-back order

@@ -177,11 +177,13 @@ template <int W, int BA, int V> __device__ __forceinline__ uint32_t tok_run_byte
 // K1: k_dec_map -- windowed exit rows per chunk, segment composition, chain resolution (anchors)
 constexpr int DM_T = 256;
 constexpr int DM_SCOUT = 8;                // true-chain tokens the scout follows at most
+constexpr int DM_FARC = 128;               // entries of the composer's far-token cache
+constexpr int DM_SAMPLE = 12;              // true tokens sampled for the dense / sparse decision
+constexpr uint32_t DM_SPARSE_LEN = 256;    // mean stream bytes per sampled token from which the stream counts as sparse
 constexpr uint32_t DEC_HB = 64;            // the unit one thread sweeps
 __device__ __forceinline__ uint32_t skew16h(uint32_t x) { return x + ((x >> 6) << 1); }   // u16 index, one pad word per 64 entries
 constexpr uint32_t DEC_EXH_ELEMS = DEC_CB + (DEC_CB / 64 + 1) * 2;
 constexpr uint32_t DEC_IMG_BYTES = DEC_CB + DEC_IMG_PAD + 64;
-constexpr uint32_t DM_STAGE_ROWS = 20;     // segment rows the resolver stages at a time
 
 struct DecMapSmem
 {
@@ -190,7 +192,11 @@ struct DecMapSmem
   alignas(8) unsigned long long mbar;
   uint32_t flag, pos, gBase, done;
   uint32_t nScout, scP[DM_SCOUT], scN[DM_SCOUT];     // the scout's jumps: token start, next token start
+  uint8_t segSkip[DEC_SEG];                          // composer: skip flags of the segment's chunks
+  uint32_t mode;                                     // 1: sparse stream (segment tables), 0: dense (window rows)
+  unsigned long long farCache[DM_FARC];              // composer: far token (chunk in segment << 14 | position) << 32 | where it ends
 };
+constexpr uint32_t DM_STAGE_ROWS = 20;     // segment rows the (dense-mode) resolver stages at a time
 static_assert(DEC_IMG_BYTES % 16 == 0 && DEC_IMG_BYTES + DEC_EXH_ELEMS * 2 >= DM_STAGE_ROWS * DEC_WINC * 4, "rows fit the image + table area");
 static_assert(DEC_SEG * DEC_WINC * 4 <= DEC_IMG_BYTES + DEC_EXH_ELEMS * 2, "segment rows fit");
 
@@ -206,6 +212,28 @@ __device__ __forceinline__ uint32_t dec_code_abs(uint32_t code, uint32_t c0, con
   return kind == TK_OK ? c0 + p + len : (kind == TK_END ? POS_END : POS_BAD);
 }
 
+// a far-jumping token parsed from the stream: ONE round trip for the seven aligned words that hold its 24-byte window (the buffer is
+// readable up to the next 16-byte boundary after the stream: words beyond that read as zero), then the register parse of phase A
+template <int W, int BA, int V>
+__device__ __forceinline__ uint32_t dec_far_abs_inl(const uint8_t *in, uint32_t tp, bool single, uint32_t clen)
+{
+  const uint32_t endAligned = (clen + 15u) & ~15u, base = tp & ~3u, sh = (tp & 3u) * 8u;
+  uint32_t w[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) w[k] = (base + 4u * k < endAligned) ? __ldcg(reinterpret_cast<const uint32_t *>(in + base) + k) : 0u;
+  TokWin x;
+#pragma unroll
+  for (int k = 0; k < 6; k++) x.w[k] = __funnelshift_r(w[k], w[k + 1], sh);
+  uint32_t kind; TokF f;
+  const uint32_t len = toklen<W, BA, V>(x, single, clen - tp, kind, f);
+  return kind == TK_OK ? tp + len : (kind == TK_END ? POS_END : POS_BAD);      // tp + len <= clen (the token fits)
+}
+template <int W, int BA, int V>
+__device__ __noinline__ uint32_t dec_far_abs(const uint8_t *in, uint32_t tp, bool single, uint32_t clen)
+{
+  return dec_far_abs_inl<W, BA, V>(in, tp, single, clen);
+}
+
 // the same for a code read back from the chunk table in global memory: far-jumping tokens are parsed from the stream
 template <int W, int BA, int V>
 __device__ __forceinline__ uint32_t dec_tab_abs(const DecBufs &D, uint32_t code, uint32_t c0, bool single, uint32_t clen)
@@ -213,11 +241,7 @@ __device__ __forceinline__ uint32_t dec_tab_abs(const DecBufs &D, uint32_t code,
   constexpr Spec sp = make_spec(W, BA, V);
   if (code < EX_FAR) return c0 + code;
   if (code < EX_FARP) return code == EX_END ? POS_END : POS_BAD;
-  const uint32_t tp = c0 + (code & 0x3FFFu);
-  Tok tk; dec_parse(sp, single, D.in + tp, (uint64_t)clen - tp, tk);
-  if (!tk.valid) return POS_BAD;
-  if (tk.last) return POS_END;
-  return tp + tk.hdrLen + tk.litLen;                                  // <= clen (the token fits)
+  return dec_far_abs_inl<W, BA, V>(D.in, c0 + (code & 0x3FFFu), single, clen);
 }
 
 // the resolver: follows the true chain from the stream start, leaves an anchor in every chunk it visits
@@ -234,44 +258,74 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
 #else
 #define HSRLE_RT(i) do { } while (0)
 #endif
-  if (t == 0) { S.pos = hs.first; S.gBase = 0; S.done = 0; }
-  __syncthreads();
-  uint32_t lastAnchor = 0xFFFFFFFFu;
-  for (;;)
+  if (S.mode)
   {
-    const uint32_t g0 = S.gBase;
-    // stage the rows of the first chunks of segments [g0, g0 + DM_STAGE_ROWS)
-    const uint32_t nr = min((uint32_t)DM_STAGE_ROWS, nSeg - g0);
-    for (uint32_t i = t; i < nr * DEC_WINC; i += DM_T)
-    {
-      const uint32_t g = g0 + i / DEC_WINC, w = i % DEC_WINC;
-      rows[i] = __ldcg(D.sufMap + (size_t)g * DEC_SEG * DEC_WINC + w);
-    }
-    __syncthreads();
+    // one look-up per SEGMENT the chain visits: segTab holds, for every stream position, where the chain through it leaves its segment
     if (t == 0)
     {
-      uint32_t pos = S.pos;
-      bool fin = false;
+      uint32_t pos = hs.first;
       for (uint32_t guard = 0;; guard++)
       {
-        if (guard > (1u << 24)) { pos = POS_BAD; fin = true; D.cnt->chainBad = 0x600; break; }   // (every step advances by at least one chunk: never reached)
-        if (pos >= POS_SPECIAL) { fin = true; break; }
-        if (pos >= clen) { pos = POS_BAD; fin = true; break; }
-        const uint32_t c = pos / DEC_CB, o = pos - c * DEC_CB, g = c / DEC_SEG;
-        if (g >= g0 + nr) break;                                    // beyond the staged rows: stage again from there
-        if (c != lastAnchor) { D.anchorAt[c] = pos; lastAnchor = c; }
-        if (o < DEC_WINC)
-        {
-          if (c == g * DEC_SEG) pos = rows[(g - g0) * DEC_WINC + o];
-          else pos = __ldcg(D.sufMap + (size_t)c * DEC_WINC + o);
-        }
-        else pos = __ldcg(D.skipFlag + c) ? POS_BAD : dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)c * DEC_CB + o), c * DEC_CB, single, clen);   // after a long literal
+        if (guard > nSeg + 1u) { pos = POS_BAD; D.cnt->chainBad = 0x600; break; }   // (every step leaves a segment: never reached)
+        if (pos >= POS_SPECIAL) break;
+        if (pos >= clen) { pos = POS_BAD; break; }
+        const uint32_t c = pos / DEC_CB;
+        if (__ldcg(D.skipFlag + c)) { pos = POS_BAD; break; }          // (the true chain never lands in a chunk one of its own tokens jumps over)
+        D.anchorAt[c] = pos;
+        pos = __ldcg(D.segTab + pos);
       }
       S.pos = pos;
-      if (fin) S.done = 1; else S.gBase = pos / DEC_CB / DEC_SEG;
     }
     __syncthreads();
-    if (S.done) break;
+  }
+  else
+  {
+    if (t == 0) { S.pos = hs.first; S.gBase = 0; S.done = 0; }
+    __syncthreads();
+    uint32_t lastAnchor = 0xFFFFFFFFu;
+    for (;;)
+    {
+      const uint32_t g0 = S.gBase;
+      // stage the rows of the first chunks of segments [g0, g0 + DM_STAGE_ROWS)
+      const uint32_t nr = min((uint32_t)DM_STAGE_ROWS, nSeg - g0);
+      for (uint32_t i = t; i < nr * DEC_WINC; i += DM_T)
+      {
+        const uint32_t g = g0 + i / DEC_WINC, w = i % DEC_WINC;
+        rows[i] = __ldcg(D.sufMap + (size_t)g * DEC_SEG * DEC_WINC + w);
+      }
+      __syncthreads();
+      if (t == 0)
+      {
+        uint32_t pos = S.pos;
+        bool fin = false;
+        for (uint32_t guard = 0;; guard++)
+        {
+          if (guard > (1u << 24)) { pos = POS_BAD; fin = true; D.cnt->chainBad = 0x600; break; }   // (every step advances by at least one chunk: never reached)
+          if (pos >= POS_SPECIAL) { fin = true; break; }
+          if (pos >= clen) { pos = POS_BAD; fin = true; break; }
+          const uint32_t c = pos / DEC_CB, o = pos - c * DEC_CB, g = c / DEC_SEG;
+          if (g >= g0 + nr) break;                                    // beyond the staged rows: stage again from there
+          if (c != lastAnchor) { D.anchorAt[c] = pos; lastAnchor = c; }
+          if (o < DEC_WINC)
+          {
+            if (c == g * DEC_SEG) pos = rows[(g - g0) * DEC_WINC + o];
+            else pos = __ldcg(D.sufMap + (size_t)c * DEC_WINC + o);
+          }
+          else if (__ldcg(D.skipFlag + c)) pos = POS_BAD;
+          else
+          { // after a long literal.  The token at the landing first: when it leaves the chunk by itself (long literals come in
+            // sequences) that is the next landing, one round trip; else the chunk table takes over from where it ends
+            const uint32_t nx = dec_far_abs_inl<W, BA, V>(D.in, pos, single, clen);
+            if (nx < POS_SPECIAL && nx / DEC_CB == c) pos = dec_tab_abs<W, BA, V>(D, __ldcg(D.chunkTab + (size_t)nx), c * DEC_CB, single, clen);
+            else pos = nx;
+          }
+        }
+        S.pos = pos;
+        if (fin) S.done = 1; else S.gBase = pos / DEC_CB / DEC_SEG;
+      }
+      __syncthreads();
+      if (S.done) break;
+    }
   }
   if (t == 0 && S.pos != POS_END) D.cnt->chainBad = 1;
   __threadfence();
@@ -319,7 +373,7 @@ __device__ void dec_resolve(const DecBufs &D, const DecScalars &hs, DecMapSmem &
 }
 
 template <int W, int BA, int V>
-__global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
+__global__ void __launch_bounds__(DM_T, 4) k_dec_map(const DecBufs D)
 {
   constexpr Spec sp = make_spec(W, BA, V);
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -512,10 +566,90 @@ __global__ void __launch_bounds__(DM_T) k_dec_map(const DecBufs D)
     uint32_t live = 0;
     for (uint32_t i = 0; i < nHere; i++) live += __ldcg(D.skipFlag + cFirst + i) ? 0u : 1u;
     S.pos = live;
+    // Window rows or segment tables?  Sampled on the first true tokens (every composer gets the same answer).  Chains of short tokens
+    // land inside the entry windows: window rows are all the resolver needs (the narrow codecs on compressible data).  With long
+    // literals nearly every landing is deep inside a chunk and the resolver makes one or two dependent look-ups per TOKEN; a table with
+    // the exit of the segment for EVERY position makes that one look-up per SEGMENT.  Building it costs a pass over the chunk tables,
+    // per chunk and one chunk of a segment after the other: it pays when there is at least a token per chunk to save (mean token
+    // below the chunk size) and there are enough segments to keep the SMs busy (measured: 3.0 -> 1.8 ms on a 1-GiB run-mixed frame
+    // of the 64-bit codecs; a loss for the 88 MB streams -- 67 segments -- and for 8-bit streams of the same frame: 34 643 chunks for
+    // 5 768 tokens).
+    uint32_t p = hs.first, k = 0;
+    const bool manySegs = nSeg >= gridDim.x / 8u;
+    for (; manySegs && k < (uint32_t)DM_SAMPLE && p < clen; k++)
+    {
+      const uint32_t nx = dec_far_abs_inl<W, BA, V>(D.in, p, single, clen);
+      if (nx >= clen) break;                                          // (also POS_END / POS_BAD)
+      p = nx;
+    }
+    const uint32_t meanTok = k ? (p - hs.first) / k : 0u;
+    S.mode = (k >= 4 && meanTok >= DM_SPARSE_LEN && meanTok <= DEC_CB && manySegs) ? 1u : 0u;
   }
   __syncthreads();
-  if (S.pos != 0)
-  {
+#if defined(HSRLE_PHASE_TIMERS)
+  unsigned long long ct0 = 0; if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ct0));
+#endif
+  if (S.pos != 0 && S.mode)
+  { // SPARSE streams -- segment table, EVERY offset of every chunk: where the chain through that position leaves the segment (absolute position,
+    // POS_END, POS_BAD).  Chunks in reverse order: an exit into a later chunk of the segment takes that position's (final) entry.
+    // The look-ups repeat a few hundred distinct positions per chunk (chains merge): they hit in cache.
+    const uint64_t segEnd = (uint64_t)(cFirst + nHere) * DEC_CB;
+    if (t < (int)DEC_SEG) S.segSkip[t] = ((uint32_t)t < nHere) ? __ldcg(D.skipFlag + cFirst + t) : (uint8_t)1;
+    for (uint32_t i = t; i < (uint32_t)DM_FARC; i += DM_T) S.farCache[i] = ~0ull;
+    __syncthreads();
+    for (int i = (int)nHere - 1; i >= 0; i--)
+    {
+      const uint32_t ci = cFirst + (uint32_t)i;
+      if (!S.segSkip[i])
+      {
+        const uint16_t *tab = D.chunkTab + (size_t)ci * DEC_CB;
+        uint32_t *dst = D.segTab + (size_t)ci * DEC_CB;
+        constexpr int NV = (int)(DEC_CB / (DM_T * 8));
+        uint4 v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] = __ldcg(reinterpret_cast<const uint4 *>(tab + (uint32_t)(k * DM_T + t) * 8));
+#pragma unroll 1
+        for (int k = 0; k < NV; k++)
+        {
+          const uint32_t q = (uint32_t)(k * DM_T + t) * 8;
+          uint4 vv = v[0];
+#pragma unroll
+          for (int kk = 1; kk < NV; kk++) if (kk == k) vv = v[kk];
+          const uint32_t w[4] = { vv.x, vv.y, vv.z, vv.w };
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+          {
+            const uint32_t code = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+            uint32_t x;
+            if (code < EX_FAR) x = ci * DEC_CB + code;
+            else if (code < EX_FARP) x = code == EX_END ? POS_END : POS_BAD;
+            else
+            { // far-jumping token: parsed from the stream, then found in a small cache (many positions share a chain's last token)
+              const uint32_t key = ((uint32_t)i << 14) | (code & 0x3FFFu), slot = (key * 2654435761u) >> 25;
+              const unsigned long long e = S.farCache[slot];
+              if ((uint32_t)(e >> 32) == key) x = (uint32_t)e;
+              else { x = dec_far_abs<W, BA, V>(D.in, ci * DEC_CB + (code & 0x3FFFu), single, clen); S.farCache[slot] = ((unsigned long long)key << 32) | x; }
+            }
+            if (x < POS_SPECIAL)
+            {
+              if (x >= clen) x = POS_BAD;
+              else if ((uint64_t)x < segEnd) x = S.segSkip[x / DEC_CB - cFirst] ? POS_BAD : D.segTab[x];   // (written by this CTA: plain, cached load)
+            }
+            o[j] = x;
+          }
+          reinterpret_cast<uint4 *>(dst + q)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          reinterpret_cast<uint4 *>(dst + q)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+#if defined(HSRLE_PHASE_TIMERS)
+  if (D.dbg && t == 0) { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); atomicMax(D.dbg + 3110, (uint32_t)(now_ - ct0)); atomicAdd(D.dbg + 3111, 1u); }
+#endif
+  if (S.pos != 0 && !S.mode)
+  { // DENSE streams -- window rows: exit of the segment per entry offset < DEC_WINC of every chunk (the resolver's other landings take the chunk tables)
     for (uint32_t i = t; i < nHere * DEC_WINC; i += DM_T)
     {
       const uint32_t ci = cFirst + i / DEC_WINC, w = i % DEC_WINC;

@@ -171,8 +171,11 @@ class SlicedEncoder:
             self._gather()
             self.state_rounds += 1
             changed = self.t_all.view(self.world, MSG_WORDS)[:self.active, 6]
-            if not bool(changed.any().item()) or self.state_rounds > self.world + 1:
+            if not bool(changed.any().item()):
                 break
+            if self.state_rounds > self.world + 1:
+                # a state travels at least one slice per round: world rounds always suffice.  More means the exchange is broken.
+                raise RuntimeError(f"sliced encode: incoming states did not settle after {self.state_rounds} rounds (world {self.world})")
         if on:
             eng.phase(job, 3)
         self._gather()

@@ -179,7 +179,9 @@ size_t hsrle_decompress_workspace_size(int codec, uint32_t inSize, uint32_t outS
 /* Device-resident, stream-ordered, no host synchronisation.  All pointers are device pointers, 16-byte
  * aligned.  dResult[0] receives the byte count (0 on error), dResult[1] a status code (0 = ok,
  * 1 = output too small, 2 = corrupt stream, 3 = bad argument/header); dResult[2..7] diagnostics.
- * Returns 0 when the work was enqueued, non-zero on a launch/argument error. */
+ * Returns 0 when the work was enqueued, non-zero on a launch/argument error.
+ * Readable extent: the kernels read whole 16-byte vectors, so dIn must be readable up to the next 16-byte boundary after
+ * dIn + inSize (any cudaMalloc'ed buffer is: allocations are 256-byte granular); the bytes past inSize are never used. */
 int hsrle_compress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
                                 void *dWorkspace, size_t workspaceSize, uint32_t *dResult, void *cudaStream);
 int hsrle_decompress_device_async(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *dOut, uint32_t outSize,
