@@ -107,12 +107,13 @@ static const EncKernels *enc_kernels_for(int codec)
 // (multiple of 4) that minimises waves x tile time, with a fixed per-tile cost (ticket, look-back, two barriers) of
 // about two steps.  Depends only on the vector count and the SM count: deterministic per call, as the workspace layout
 // needs it.
-static uint32_t enc_scan_steps(uint32_t nVec)
+static uint32_t enc_scan_steps(uint32_t nVec, bool pow2Only = false)
 {
   const uint64_t slots = (uint64_t)num_sms() * 4;
   uint32_t best = E1_STEPS; uint64_t bestCost = ~0ull;
   for (uint32_t steps = 8; steps <= (uint32_t)E1_STEPS; steps += 4)
   {
+    if (pow2Only && (steps & (steps - 1))) continue;
     const uint64_t tiles = ((uint64_t)nVec + (uint64_t)E1_T * steps - 1) / ((uint64_t)E1_T * steps);
     const uint64_t waves = (tiles + slots - 1) / slots;
     const uint64_t cost = waves * (steps + 2);
@@ -140,14 +141,14 @@ static int enc_fix_grid(const EncBufs &B, int sms)
   return B.maxSC <= 4 * FIX_SOLO ? 1 : std::min<int>(sms, 1 + (int)(B.maxSC / 64));
 }
 
-static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t *zeroBytes)
+static size_t enc_carve(EncBufs &B, const Spec &sp, uint32_t n, void *ws, size_t *zeroBytes, bool sliceTiles = false)
 {
   Carver cv{ (uint8_t *)ws, 0 };
   B.n = n;
   B.nVec = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
   B.lastVec = (n - 1) >> 4;
-  B.scanSteps = enc_scan_steps(B.nVec);
-  B.nTiles = (B.nVec + E1_T * B.scanSteps - 1) / (E1_T * B.scanSteps);
+  B.scanSteps = enc_scan_steps(B.nVec, sliceTiles);
+  B.nTiles = (B.nVec + E1_T * B.scanSteps - 1) / (E1_T * B.scanSteps) + (sliceTiles ? 1u : 0u);   // (slices: the last rank's vector count is a little larger)
   B.maxRuns = n / (sp.minM + 1) + 2;
   B.maxSC = B.maxRuns / E2_SCR + 2;
   const size_t maxChunks = (size_t)B.maxSC * E2_T;
@@ -283,7 +284,7 @@ static int enc_enqueue(int codec, const uint8_t *dIn, uint32_t n, uint8_t *dOut,
 static size_t slice_carve(EncBufs &B, const Spec &sp, uint32_t n, uint32_t lo, uint32_t hi, int rank, int world, void *ws, size_t *zeroBytes)
 {
   const uint32_t len = hi - lo;
-  const size_t base = enc_carve(B, sp, len ? len : 1, ws, zeroBytes);     // record / chunk capacities from the slice length
+  const size_t base = enc_carve(B, sp, len ? len : 1, ws, zeroBytes, true);     // record / chunk capacities from the slice length
   Carver cv{ (uint8_t *)ws, base };
   B.sliceIn = cv.take<SliceState>(1);
   B.n = n;
@@ -293,7 +294,9 @@ static size_t slice_carve(EncBufs &B, const Spec &sp, uint32_t n, uint32_t lo, u
   const uint32_t nVecGlobal = (uint32_t)(((uint64_t)n + 1 + 15) / 16);
   const uint32_t vecs = last ? nVecGlobal - B.vecBase : len / 16;
   B.nVec = vecs;
-  B.scanSteps = enc_scan_steps(vecs);
+  // a slice's tiles must end exactly where the slice ends (vectors past the cut belong to the next rank: a tile that reaches over it would
+  // count their run boundaries): tile sizes that divide the 128-KiB slice alignment only (32 / 64 / 128 KiB)
+  // (enc_carve picked among those -- sliceTiles -- and sized the look-back words for at least this many tiles)
   B.nTiles = (vecs + E1_T * B.scanSteps - 1) / (E1_T * B.scanSteps);
   B.lastVec = last ? (n - 1) >> 4 : hi / 16;        // non-last ranks may load the first vector of the tail halo
   B.maxRuns += 2;

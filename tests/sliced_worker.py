@@ -100,7 +100,12 @@ def main():
         engine = SimEngine()
     from hsrle_b200 import sliced
     bad = 0
-    for label, data in inputs(which):
+    ins = inputs(which)
+    if mode != "sim" and which == "all":
+        # slices of tens of MB: the scan picks its tile size per call from the slice length (hsrle_api.cu: enc_scan_steps) -- sizes
+        # that do not divide the slice made the last tile reach over the cut (found by the 4-GPU run of the 1-GiB frame)
+        ins.append(("big", gen_run_mixed(world * (24 << 20) + 4321, seed=9)))
+    for label, data in ins:
         n = len(data)
         for name in codecs:
             enc = sliced.SlicedEncoder(name, n, engine=engine)

@@ -446,3 +446,49 @@ def test_corrupt_token_streams_fail_safely(hs, name):
             r = hs.decompress_device(name, t_s, len(bad), t_dec, n)
             assert r in (0, n), (name, r)
             assert bool((t_dec[n:] == 0xEE).all()), name + ": wrote past the declared output size"
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name", ["rle8_multi", "rle8_7symlut", "rle16_3symlut_byte", "rle32_byte_packed", "rle48_7symlut_sym", "rle64_byte",
+                                  "rle64_3symlut_byte"])
+def test_segment_table_mode_of_the_decoder(hs, name):
+    """A 48 MiB stream of literals of 256 B .. 8 KiB between short runs: the mean token is between 256 B and a chunk and the stream
+    has more segments than the GPU has SMs, so k_dec_map's composers build the all-position segment tables and the resolver
+    takes one look-up per segment (hsrle_dec_kernels.cuh: S.mode == 1) -- with and without a LUT in the aggregate."""
+    codec = CODEC_BY_NAME[name]
+    rng = np.random.default_rng(123)
+    W = codec.W
+    parts, total = [], 0
+    while total < 48 << 20:
+        ll = int(2 ** rng.uniform(8, 13))
+        parts.append(rng.integers(0, 256, size=ll, dtype=np.uint8))
+        rl = int(rng.integers(4, 40))
+        parts.append(np.tile(rng.integers(0, 256, size=W, dtype=np.uint8), rl))
+        total += ll + rl * W
+    data = np.concatenate(parts)
+    want = oracle_compress(codec, data)
+    assert len(want) > 40 << 20                                         # >= 148 segments of 256 KiB
+    got = gpu_enc(hs, codec, data)
+    assert np.array_equal(got, want), name
+    r, dec = gpu_dec(hs, codec, want, len(data))
+    assert r == len(data) and np.array_equal(dec, data), name
+
+
+@pytest.mark.parametrize("name", ["rle8_3symlut", "rle8_7symlut"])
+def test_lut_walk_fallbacks(hs, name):
+    """The 8-bit LUT encoders take the table at every super-chunk start from the stretch walk (hsrle_enc_lutwalk.cuh) -- unless the
+    input has more than LW_CAP symbol changes between candidate runs, or a stretch of more than LW_BACK records none of which
+    is certain.  Then the plain state guess and the verify / repair rounds alone must produce the same stream."""
+    codec = CODEC_BY_NAME[name]
+    rng = np.random.default_rng(31)
+    many_symbols = gen_fuzz(rng, 6 << 20, max_sym=40, p_run=0.3)         # ~80 K stretch boundaries: over the cap
+    noise = (np.arange(300, dtype=np.uint32) * 7 % 251 + 1).astype(np.uint8)   # no two equal neighbours
+    piece = np.concatenate([noise, np.full(3, 0x61, dtype=np.uint8)])           # a 3-byte run every 303 bytes: never emitted
+    long_uncertain = np.concatenate([np.tile(piece, 4000), gen_dct(1 << 20, seed=8), np.tile(piece, 300)])
+    sparse = gen_dct(5 << 20, seed=9)                                     # the walk's own territory
+    for data in (many_symbols, long_uncertain, sparse):
+        want = oracle_compress(codec, data)
+        got = gpu_enc(hs, codec, data)
+        assert len(got) == len(want) and np.array_equal(got, want), (name, len(got), len(want))
+        r, dec = gpu_dec(hs, codec, got, len(data))
+        assert r == len(data) and np.array_equal(dec, data)
