@@ -3,25 +3,30 @@
 // The stream has no sync markers: token k starts where token k-1 ends.  The decoder finds the token chain
 // speculatively per chunk (16 KiB of stream) and resolves it with a merge of windowed exit maps:
 //
-//   K1  k_dec_map<codec>   one CTA per chunk.  The chunk image arrives in shared memory by a 1-D bulk copy (TMA); a token is
+//   K1  k_dec_map<codec>   CTAs loop over chunks (grid = min(chunks, 8 per SM)).  Once per CTA a SCOUT follows the true chain
+//                          from the stream start while its tokens jump over whole chunks: chunks jumped over get a flag and
+//                          nothing else.  Per chunk: the image arrives in shared memory by a 1-D bulk copy (TMA); a token is
 //                          parsed at EVERY byte offset; a blocked reverse sweep turns "where does the token at p end" into
-//                          "where does the chain that starts at p leave its 64 / 128 / 256 / 512-byte block", then -- only for
-//                          the first DEC_WIN offsets of every 1-KiB sub-chunk, the only places a chain can enter it unless a
-//                          long literal spans the boundary -- "... its sub-chunk" and "... the chunk".  Nothing per-position
-//                          leaves the SM: the chunk publishes its 16 windowed sub-chunk exit rows (subMap, u16 codes) and one
-//                          windowed chunk exit row (chunkMap, absolute positions).
-//                          The last CTA of every 32-chunk segment composes the segment's rows in reverse (sufMap: where does the
-//                          chain entering chunk c at window offset w leave the SEGMENT, or land outside a window), and the last
-//                          CTA of all follows the true chain from the stream start through those rows -- one look-up per
-//                          segment, rows staged in shared memory; out-of-window landings (after a long literal) continue by
-//                          parsing -- and leaves an ANCHOR (the exact position of a true token start) in every chunk it visits.
-//   K2  k_dec_emit<codec>  persistent CTAs take chunks in order.  The chunk's first true token start follows from the nearest
-//                          anchor (a few window-row hops); 16 lanes walk the chunk's 16 sub-chunks from their entries (sub-chunk
-//                          rows), giving per-token records, output bytes and symbol / LUT state of the chunk; a decoupled
-//                          look-back over the chunks yields the output offset and incoming symbol state; the tokens are
-//                          expanded into a 16-KiB shared-memory image of the output (byte-exact, any alignment) that is flushed
-//                          with aligned 16-byte stores.  Token parts that span whole output tiles of 256 KiB and more become
-//                          grid-wide operations every idle CTA helps with (literal source staged by bulk copies).
+//                          "where does the chain that starts at p leave its 64 / 128 / 256 / 512-byte block", then -- for the
+//                          first DEC_WIN offsets of every 1-KiB sub-chunk -- "... its sub-chunk" (subMap: the rows K2 walks the
+//                          sub-chunks from) and, for every offset, "... the chunk" (chunkTab, u16 codes).
+//                          The last CTA of every 16-chunk segment composes the segment's exits in reverse chunk order: window
+//                          rows (sufMap: chain entering chunk c at offset w < DEC_WINC leaves the SEGMENT at ...) for streams
+//                          of short tokens, or the same for EVERY position (segTab) for streams of long literals with many
+//                          segments -- decided per call from the first true tokens, identically by every composer.
+//                          The last CTA of all is the RESOLVER: one thread follows the true chain from the stream start
+//                          (window rows / chunk table or a direct parse after a long literal / one segTab look-up per
+//                          segment) and leaves an ANCHOR in the chunks it lands in; one thread per segment derives every
+//                          chunk's first true token start from the anchors (chunkEntry); the chunks that have one are listed
+//                          in stream order (liveList).
+//   K2  k_dec_emit<codec>  persistent CTAs take the LIVE chunks in order.  Thread 0 hops from the chunk's entry to every
+//                          sub-chunk's entry (sub-chunk rows); 16 lanes walk the 16 sub-chunks, giving token starts, output
+//                          bytes and symbol / LUT state of the chunk; a decoupled look-back over the live chunks yields the
+//                          output offset and incoming symbol state; the tokens are expanded into a 16-KiB shared-memory image
+//                          of the output (byte-exact, any alignment) that is flushed with aligned 16-byte stores.  Token parts
+//                          that cover 64 KiB of whole output tiles and more become grid-wide operations: registered with one
+//                          atomic (operation index and first piece number together), taken in 64-KiB pieces in one global
+//                          order by every CTA that is out of chunks.
 //
 // Reference behaviour restated (never copied): token parse src/rleX_extreme_cpu_decode.h:43-163, src/rleX_Xsl.h:580-784,
 // src/rle8_extreme_cpu.h:1558-1632,2020-2087; header checks src/rle8_extreme_cpu.h:704-761, src/rleX_extreme_cpu.h:84-91; the

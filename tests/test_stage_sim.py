@@ -1,5 +1,6 @@
 """CPU tests of the product's stage logic.  tests/sim/sim_pipeline.cpp drives the SAME per-item stage
-functions the CUDA kernels wrap (hypersonic-rle-kit_b200/csrc/hsrle_stages.cuh) from host loops and
+functions of the ENCODER kernels (hsrle_core.cuh, hsrle_enc.cuh) and of the round-1 decoder design (tests/sim/hsrle_dec_v1.cuh, kept as a
+second, independent decoder model -- the product decoder is covered by the GPU parity tests) from host loops and
 must reproduce the oracle bit for bit.  The simulator is a test tool; it is not part of the product."""
 import ctypes
 import os
