@@ -388,6 +388,10 @@ static int dec_enqueue(int codec, const uint8_t *dIn, uint32_t inSize, uint8_t *
   if (need > wsSize) { g_err = "workspace too small"; return 1; }
   D.in = dIn; D.out = dOut; D.dResult = dResult;
   D.emitGrid = (uint32_t)g_emitGrid[current_dev()][codec];
+  { // tests force either way of composing the segment exits (the result must not depend on it)
+    const char *m = getenv("HSRLE_DEC_MODE");
+    D.modeOverride = !m ? 0u : (!strcmp(m, "rows") ? 1u : (!strcmp(m, "segtab") ? 2u : 0u));
+  }
   if (!cuda_ok(cudaMemsetAsync(ws, 0, zeroBytes, st), "memset")) return 2;
   static const bool dbg = getenv("HSRLE_DEBUG") != nullptr;
   static uint32_t *hDbg = nullptr;

@@ -210,6 +210,7 @@ struct DecBufs
   void *aggBuf, *incBuf;    // [nChunks] DecAgg<K>: per-chunk totals / inclusive prefixes
   DecBigOp *bigList;
   uint32_t bigCap;
+  uint32_t modeOverride;    // 0: K1's composers decide (rows / segment tables); 1: rows; 2: segment tables (tests: HSRLE_DEC_MODE)
   uint32_t *pieceOp;        // [pieceCap] (zeroed) piece number -> operation index + 1, written when the operation is registered
   uint32_t pieceCap;
   uint32_t *dResult;

@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(DM_T, 4) k_dec_map(const DecBufs D)
     // of the 64-bit codecs; a loss for the 88 MB streams -- 67 segments -- and for 8-bit streams of the same frame: 34 643 chunks for
     // 5 768 tokens).
     uint32_t p = hs.first, k = 0;
-    const bool manySegs = nSeg >= gridDim.x / 8u;
+    const bool manySegs = gridDim.x >= 256u && nSeg >= gridDim.x / 8u;   // (the grid is 8 CTAs per SM when there are that many chunks)
     for (; manySegs && k < (uint32_t)DM_SAMPLE && p < clen; k++)
     {
       const uint32_t nx = dec_far_abs_inl<W, BA, V>(D.in, p, single, clen);
@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(DM_T, 4) k_dec_map(const DecBufs D)
     }
     const uint32_t meanTok = k ? (p - hs.first) / k : 0u;
     S.mode = (k >= 4 && meanTok >= DM_SPARSE_LEN && meanTok <= DEC_CB && manySegs) ? 1u : 0u;
+    if (D.modeOverride) S.mode = D.modeOverride - 1u;
   }
   __syncthreads();
 #if defined(HSRLE_PHASE_TIMERS)

@@ -81,8 +81,17 @@ __global__ void __launch_bounds__(LW_T) k_enc_lut_stretch(const EncBufs B)
 #pragma unroll
       for (int q = 0; q < LW_PER / 4; q++)
       {
-        const uint4 v = *reinterpret_cast<const uint4 *>(sym + j0 + 4 * q);      // (the array is padded: hsrle_api.cu enc_carve)
-        s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+        const uint32_t jq = j0 + 4 * q;
+        if (jq + 3 < nRuns)
+        {
+          const uint4 v = *reinterpret_cast<const uint4 *>(sym + jq);
+          s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+        }
+        else
+        { // the group that holds the last record: word by word, nothing past it is read
+#pragma unroll
+          for (int i = 0; i < 4; i++) s[4 * q + i] = (jq + i < nRuns) ? sym[jq + i] : 0u;
+        }
       }
       uint32_t prev = j0 ? sym[j0 - 1] : ~s[0];
 #pragma unroll

@@ -492,3 +492,18 @@ def test_lut_walk_fallbacks(hs, name):
         assert len(got) == len(want) and np.array_equal(got, want), (name, len(got), len(want))
         r, dec = gpu_dec(hs, codec, got, len(data))
         assert r == len(data) and np.array_equal(dec, data)
+
+
+@pytest.mark.parametrize("codec", CODECS, ids=lambda c: c.name)
+def test_decoder_exit_composition_either_way(hs, codec, monkeypatch):
+    """k_dec_map composes the exits of a segment as window rows or as all-position segment tables (chosen per call from the stream);
+    HSRLE_DEC_MODE forces one: every codec must decode the same streams to the same bytes either way."""
+    rng = np.random.default_rng(2024 + codec.W)
+    datas = [gen_fuzz(rng, 300000, long_every=5), gen_run_mixed(1 << 20, seed=3, max_run_log2=14, max_lit_log2=12), gen_dct(600000, seed=11)]
+    for data in datas:
+        stream = oracle_compress(codec, data)
+        for mode in ("rows", "segtab"):
+            monkeypatch.setenv("HSRLE_DEC_MODE", mode)
+            r, dec = gpu_dec(hs, codec, stream, len(data))
+            assert r == len(data) and np.array_equal(dec, data), (codec.name, mode, len(data))
+    monkeypatch.delenv("HSRLE_DEC_MODE", raising=False)
