@@ -299,7 +299,7 @@ def run_configs1(args):
 
     # inputs rotated over 4 distinct copies (352 MB > 126 MB L2) so no call finds its input in L2
     NCOPY = 4
-    NSTREAM = args.streams
+    NSTREAM = args.streams if args.streams > 0 else 12
     t_in = [torch.from_numpy(data).to(dev) for _ in range(NCOPY)]
     t_comp = {c: torch.empty(cap, dtype=torch.uint8, device=dev) for c in CODEC_SET}
     ws_size = max(max(hs.compress_workspace_size(c, n) for c in CODEC_SET), max(hs.decompress_workspace_size(c, cap, n) for c in CODEC_SET))
@@ -597,17 +597,23 @@ def run_configs3(args):
         refs.update(r)
     ref_s = time.time() - t0
 
-    pool = fr.StreamPool(CODEC_SET3, FB, device=dev, streams=min(args.streams, 4))
+    # streams in flight per rank: every one holds a workspace of ~10 GB for a 2^30-byte frame (and rank 0 of a one-GPU run already holds
+    # 16 input frames and 48 compressed ones)
+    n_streams = args.streams if args.streams > 0 else (4 if len(mine) > 8 else 6)
+    pool = fr.StreamPool(CODEC_SET3, FB, device=dev, streams=n_streams)
 
     def run_sequence(ids, steps, check):
         """encode + decode of the frames `ids` with every codec, `steps` times; returns ms (CUDA events on the launching
         stream).  check: compare every stream with the reference's and every decoded frame with its input."""
         codecs = {c: fr.FrameCodec(c, [FB] * len(ids), pool=pool) for c in CODEC_SET3}
-        outs = [torch.empty(FB + 128, dtype=torch.uint8, device=dev) for _ in range(min(len(ids), len(pool.streams)))]
+        outs_s = [torch.empty(FB + 128, dtype=torch.uint8, device=dev) for _ in pool.streams]     # one output buffer per pool stream
+        outs = outs_s[:max(1, min(len(ids), len(pool.streams)))]
         ins = [t_frames[f] for f in ids]
 
         def step(verify=False):
             for c, fc in codecs.items():
+                if not verify:
+                    break
                 fc.encode_async(ins)
                 if verify:
                     sizes = fc.finish_encode()
@@ -622,8 +628,13 @@ def run_configs3(args):
                         fc.decode_async(outs, grp); fc.finish_decode(grp)
                         for k, i in enumerate(grp):
                             assert torch.equal(outs[k][:FB], ins[i]), f"{c}: frame {ids[i]} does not decode back"
-                else:
-                    fc.decode_async(outs)
+            if not verify:
+                # the timed form: every (codec, frame) pair is its own chain -- encode, then decode, on one pool stream -- and all chains of
+                # the step overlap (one fork / join per step, not per codec and direction)
+                pool.fork()
+                for ci, fc in enumerate(codecs.values()):
+                    fc.roundtrip_async(ins, outs_s, offset=ci * max(1, len(pool.streams) // len(codecs)))
+                pool.join()
         step(verify=check)
         for _ in range(max(args.warmup, 3) - 1):
             step()
@@ -736,6 +747,8 @@ def run_configs3(args):
     if world > 1 and not args.no_n1:
         if rank == 0:
             reps = max(1, min(args.steps, 3))
+            del codecs, step                       # (the compressed frames of the timed run: room for all 16 frames' on this rank)
+            torch.cuda.empty_cache()
             _, step1 = run_sequence(list(range(F)), 0, False)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -756,7 +769,7 @@ def run_configs3(args):
                 "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD3 if (F, FB) == (16, 1 << 30) else f"configs[3] shape, reduced: {F} frames of {FB} B", "codecs": CODEC_SET3,
-                           "frames": F, "frame_bytes": FB, "streams": args.streams,
+                           "frames": F, "frame_bytes": FB, "streams": len(pool.streams),
                            "sharding": f"frame sequence: frame f -> rank f mod {world} (independent reference-identical streams, no data-path collective); "
                                        "beside it `one_stream_slices`: one frame cut into contiguous slices over all ranks",
                            "parity": f"every frame's stream == the compiled {ref_kind}'s stream for that frame (length + sha256, computed on this box's host "
@@ -786,7 +799,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "configs1", "configs3"])
     ap.add_argument("--quick", action="store_true", help="configs1: skip the CPU baseline and the per-codec detail (sweeps)")
-    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the independent codec calls of a step are dealt to")
+    ap.add_argument("--streams", type=int, default=0, help="CUDA streams the independent codec calls of a step are dealt to (default: 12 for configs[1], 8 for configs[3])")
     ap.add_argument("--threads", type=int, default=4, help="configs1: host threads of the extra (multi-threaded) e2e figure")
     ap.add_argument("--frames", type=int, default=16, help="configs3: frames in the sequence")
     ap.add_argument("--frame-bytes", type=int, default=1 << 30, help="configs3: bytes per frame (<= 2^30)")

@@ -67,6 +67,21 @@ class StreamPool:
         self.ws = [torch.empty(ws, dtype=torch.uint8, device=self.device) for _ in self.streams]
         self.ws_bytes = ws
 
+    def fork(self):
+        """Every pool stream waits for what the current stream has enqueued so far."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        for s in self.streams:
+            s.wait_event(ev)
+
+    def join(self):
+        """The current stream waits for everything enqueued on the pool streams."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            cur.wait_event(ev)
+
 
 class FrameCodec:
     """Encoder/decoder of one rank's frames.  Buffers (compressed frames, result words) are allocated once and re-used across
@@ -135,6 +150,19 @@ class FrameCodec:
             decompress_device_async(self.name, self.comp[i], clen, outs[k % len(outs)], self.sizes[i], self.ws[j], self.res[i, 8:],
                                     self.streams[j].cuda_stream)
         self._join()
+
+    def roundtrip_async(self, frames, outs, offset=0):
+        """Enqueue encode + decode of every frame, frame i on pool stream (i + offset) mod streams: the two calls of a frame are
+        stream-ordered, different frames -- and other codecs that share the pool with another `offset` -- overlap, so the
+        latency-bound phases of one call run under the bandwidth-bound kernels of another.  No fork / join here: the caller
+        brackets a batch of such calls with pool.fork() / pool.join().  `outs[j]`: one output buffer per pool stream."""
+        from . import compress_device_async, decompress_device_async
+        for i, t in enumerate(frames):
+            j = (i + offset) % self.nstreams
+            q = self.streams[j].cuda_stream
+            compress_device_async(self.name, t, self.comp[i], self.ws[j], self.res[i, :8], q, n=self.sizes[i])
+            clen = self.clen[i] if self.clen[i] is not None else self.caps[i]
+            decompress_device_async(self.name, self.comp[i], clen, outs[j], self.sizes[i], self.ws[j], self.res[i, 8:], q)
 
     def finish_decode(self, indices=None):
         torch.cuda.current_stream(self.device).synchronize()
