@@ -747,8 +747,7 @@ def run_configs3(args):
     if world > 1 and not args.no_n1:
         if rank == 0:
             reps = max(1, min(args.steps, 3))
-            del codecs, step                       # (the compressed frames of the timed run: room for all 16 frames' on this rank)
-            torch.cuda.empty_cache()
+            torch.cuda.empty_cache()               # (the timed run's compressed frames were released above: room for all 16 frames' on this rank)
             _, step1 = run_sequence(list(range(F)), 0, False)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
