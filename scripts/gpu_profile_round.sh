@@ -12,8 +12,9 @@ timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 
 tail -c 300 gpurun_out/${TAG}_bench.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --quick > gpurun_out/${TAG}_ncu_l.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_l.log
-for C in rle32_3symlut_byte rle8_multi; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 8 -c 8 -f -o gpurun_out/${TAG}_full_$C python scripts/prof_one.py $C 0 both > gpurun_out/${TAG}_full_$C.log 2>&1
-  tail -1 gpurun_out/${TAG}_full_$C.log
-done
+# (what comes back in gpurun_out/ must stay below 64 MiB: source import only for one of the two captures)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 8 -c 8 -f -o gpurun_out/${TAG}_full_rle8_multi python scripts/prof_one.py rle8_multi 0 both > gpurun_out/${TAG}_full_rle8_multi.log 2>&1
+tail -1 gpurun_out/${TAG}_full_rle8_multi.log
+# (the second capture, rle32_3symlut_byte, is its own call: scripts/gpu_ncu.sh -- two reports do not fit the 64 MiB that come back)
 ls -la gpurun_out | tail -12
+timeout 600 python scripts/bench_edge_1gib.py > gpurun_out/${TAG}_edge.jsonl 2> gpurun_out/${TAG}_edge.err; grep -c roundtrip_ok gpurun_out/${TAG}_edge.jsonl

@@ -1,7 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --gpus 1 --workload configs3 --frames 4 --no-slices --no-e2e 2> gpurun_out/tmp_c3.err | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('configs3 4 frames N=1: value', d['value'], 'ms', d['ms_per_step'], 'streams', d['config']['streams'])"; tail -3 gpurun_out/tmp_c3.err
-python bench.py --gpus 1 --workload configs3 --no-slices --no-e2e 2> gpurun_out/tmp_c3b.err | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('configs3 16 frames N=1: value', d['value'], 'ms', d['ms_per_step'], 'streams', d['config']['streams'])"; tail -3 gpurun_out/tmp_c3b.err; nvidia-smi --query-gpu=memory.used --format=csv
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_frames.py -x -q -k "gib or huge or long_literals or edge_inputs or corrupt or frames" 2>&1 | tail -3
+timeout 300 python scripts/bench_edge_1gib.py > gpurun_out/r02bi_edge.jsonl 2> gpurun_out/r02bi_edge.err; python - <<PY
+import json
+for l in open("gpurun_out/r02bi_edge.jsonl"):
+    if l.startswith("{"):
+        d=json.loads(l); print(d["input"], d["codec"], "enc", d["enc_ms"], "dec", d["dec_ms"], d["dec_roofline"], d["roundtrip_ok"])
+PY
