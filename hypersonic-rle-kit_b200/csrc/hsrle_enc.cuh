@@ -1,18 +1,23 @@
-// hsrle_enc.cuh -- encoder pipeline of the B200 extreme-RLE codec (three phases).
+// hsrle_enc.cuh -- encoder pipeline of the B200 extreme-RLE codec (three phases; five launches).
 //
 //   E1  k_enc_scan<W,MINM>   one pass over the input: match mask M[p] = (in[p] == in[p-W]) from coalesced
 //                            16-byte-per-lane loads, run boundaries by bit tricks on 32-bit windows of M,
 //                            compaction of (start, end, first-period symbol) records with a decoupled
 //                            look-back over tiles (single pass, the input is read once).
-//   E2  k_enc_auto<codec>    the reference's per-run emit rules (hsrle_core.cuh: enc_eval) as a speculative
-//                            automaton.  A super-chunk of 2048 records is one CTA: every thread evaluates 16
-//                            records from a warmed-up guess of the incoming state, a block scan of the
-//                            chunk summaries yields the exact incoming states under the current decisions,
-//                            mismatching chunks re-run -- a fixed point of (run -> scan -> compare) is exactly
-//                            the sequential result.  The last CTA to finish scans the super-chunk summaries
-//                            (state, token bytes), marks super-chunks whose guessed incoming state was
-//                            wrong; those re-run in the next round.  After the last round a sequential
-//                            repair (one CTA, still parallel inside a super-chunk) is the exact fallback.
+//   E2  k_enc_auto<codec>    the reference's per-run emit rules (hsrle_core.cuh: enc_eval_t) as a speculative
+//                            automaton, round 0.  A super-chunk of 512 records is one WARP: every lane evaluates 16
+//                            records from a warmed-up guess of the incoming state, a warp scan of the lane
+//                            summaries yields the exact incoming states under the current decisions, mismatching
+//                            lanes re-run -- a fixed point of (run -> scan -> compare) is exactly the sequential
+//                            result inside the super-chunk.
+//       k_enc_fix<codec>     all verify / repair rounds in ONE launch: CTA 0 scans the super-chunk summaries
+//                            (state, token bytes), marks super-chunks whose assumed incoming state was wrong AND
+//                            whose decisions depended on it (LUT codecs: ScQueries), re-runs them (with helper
+//                            CTAs through tickets when there are many), verifies again; when nothing is dirty:
+//                            token offsets, header, terminator.  After the round budget an exact sequential
+//                            repair (still parallel inside a super-chunk) is the fallback.
+//       k_enc_lut_stretch / k_enc_lut_walk (8-bit LUT codecs, hsrle_enc_lutwalk.cuh): the exact table at every
+//                            super-chunk start before round 0, from a walk over the symbol changes of the records.
 //   E3  k_enc_emit<codec>    token headers + literal scatter at the scanned stream offsets.
 //       k_enc_copy_big       grid-wide copy of the few very long literals.
 //
