@@ -239,7 +239,9 @@ def run_reference_arm(args):
             "cpu_baseline": dict({"value": round(value, 4), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample + ", 1 thread"}, **info),
             "all_cores": {"value": round(work_bytes * reps / tall / 1e9, 4), "unit": UNIT, "cores": nth,
                           "sample": sample + f", {nth} threads (one codec call per thread)"},
-            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            # same workload, codec set, metric and unit as the GPU arm's line for this --gpus / --workload (configs[3]: a bounded sample of its frames)
+            "same_config": True}
     print(json.dumps(line), flush=True)
 
 
